@@ -1,0 +1,260 @@
+/*
+ * pomp_b200.h -- C-ABI of the B200-native hot path of pyOptimalMotionPlanning (pomp).
+ *
+ * The reference (krishauser/pyOptimalMotionPlanning) is pure Python and has no FFI; its
+ * "plugin boundary" is duck typing on four object families.  Every entry point below names
+ * the reference interface it replaces (file:line relative to the reference checkout):
+ *
+ *   pomp_nn_*        <- pomp/structures/nearestneighbors.py:13-141  (NearestNeighbors)
+ *   pomp_feasible    <- pomp/spaces/configurationspace.py:142,196 ; example_problems/geometric.py:56-60
+ *   pomp_edge_check* <- pomp/spaces/edgechecker.py:20-30            (EpsilonEdgeChecker.feasible)
+ *   pomp_next_state  <- pomp/spaces/controlspace.py:78,249-267 ; statespace.py:62-70 ; dubins.py:107-125
+ *   pomp_select_control <- pomp/planners/kinodynamicplanner.py:66-84 (RandomControlSelector.select)
+ *   pomp_rrt_extend  <- pomp/planners/kinodynamicplanner.py:354-411 (RRT.expand, kinematic case)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy / C++ types cross this boundary.
+ *   - every function returns 0 on success, a negative pomp_status otherwise;
+ *     pomp_last_error() returns the message of the calling thread's last failure.
+ *   - pointers without a suffix are DEVICE pointers (any CUDA allocation of the current
+ *     device, e.g. a torch tensor's data_ptr()); pointers suffixed _h are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device
+ *     entry points only enqueue work; the *_h variants synchronise before returning.
+ *   - all arithmetic is IEEE float64, one rounding per operation, no FMA contraction, in the
+ *     reference's operation order.  Indices are insertion indices.
+ *   - ties are broken by lowest insertion index; k-NN results are ordered by (distance, index),
+ *     radius results by index.
+ *   - handles are not thread-safe; the caller owns every buffer it passes.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     POMP_ERR_CUDA.
+ */
+#ifndef POMP_B200_H
+#define POMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POMP_MAX_DIM 8   /* state dimension incl. the cost coordinate (reference configs use 2..7) */
+#define POMP_MAX_COMP 8  /* components of a product space */
+
+typedef enum {
+  POMP_OK = 0,
+  POMP_ERR_INVALID = -1,  /* bad argument / unsupported descriptor */
+  POMP_ERR_CUDA = -2,     /* CUDA runtime failure (incl. no device)  */
+  POMP_ERR_CAPACITY = -3, /* caller-provided output too small        */
+  POMP_ERR_NOMEM = -4
+} pomp_status;
+
+/* ---------------------------------------------------------------- metrics -------------- */
+/* pomp/spaces/metric.py:4-23, pomp/spaces/geodesicspace.py:45-52, kinodynamicplanner.py:899-913 */
+typedef enum {
+  POMP_METRIC_EUCLIDEAN = 0,          /* vectorops.distance: sqrt(sum (a-b)*(a-b))                    */
+  POMP_METRIC_WEIGHTED_EUCLIDEAN = 1, /* WeightedEuclideanMetric(w list): sqrt(sum w_i*(a_i-b_i)**2)   */
+  POMP_METRIC_SCALED_EUCLIDEAN = 2,   /* WeightedEuclideanMetric(w scalar): w*euclidean               */
+  POMP_METRIC_L1 = 3,
+  POMP_METRIC_LINF = 4,
+  POMP_METRIC_GEODESIC_PRODUCT = 5    /* MultiGeodesicSpace.distance: sqrt(sum_c dist_c**2 * w_c)     */
+} pomp_metric_kind;
+
+typedef enum { POMP_COMP_CARTESIAN = 0, POMP_COMP_SO2 = 1 } pomp_comp_kind;
+
+typedef struct {
+  int32_t kind;                      /* pomp_metric_kind                                             */
+  int32_t dim;                       /* full point dimension, INCLUDING the cost coordinate if has_cost */
+  int32_t n_comp;                    /* GEODESIC_PRODUCT: number of components                       */
+  int32_t comp_kind[POMP_MAX_COMP];  /* pomp_comp_kind                                               */
+  int32_t comp_dim[POMP_MAX_COMP];   /* coordinates per component (SO2: 1)                           */
+  double comp_weight[POMP_MAX_COMP]; /* MultiGeodesicSpace.componentWeights                          */
+  double dim_weight[POMP_MAX_DIM];   /* WEIGHTED_EUCLIDEAN                                           */
+  double scale;                      /* SCALED_EUCLIDEAN                                             */
+  /* CostMetric wrapper (kinodynamicplanner.py:899-913): last coordinate is accumulated cost;
+     a = tree node, b = query.  d = base(a[:-1],b[:-1]); if cost_weight_set: inf when cost_max_set
+     and (a_c > cost_max or b_c > cost_max); d += max(a_c-b_c,0)*cost_weight.                       */
+  int32_t has_cost;
+  int32_t cost_weight_set;
+  int32_t cost_max_set;
+  int32_t _pad;
+  double cost_weight;
+  double cost_max;
+} pomp_metric_desc;
+
+/* ---------------------------------------------------------------- nearest neighbours ---- */
+typedef struct pomp_nn pomp_nn;
+
+const char* pomp_last_error(void);
+int pomp_version(void);
+/* number of CUDA devices visible (0 when there is none; never fails) */
+int pomp_device_count(void);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches) */
+int64_t pomp_launch_count(void);
+
+/* NearestNeighbors.__init__ (nearestneighbors.py:14-23) */
+int pomp_nn_create(const pomp_metric_desc* metric, int64_t capacity_hint, int device, pomp_nn** out);
+int pomp_nn_destroy(pomp_nn* h);
+/* NearestNeighbors.reset (:25-30) */
+int pomp_nn_reset(pomp_nn* h);
+/* NearestNeighbors.add (:32-39): append n points (row-major n x dim); indices are insertion order */
+int pomp_nn_add(pomp_nn* h, const double* pts, int64_t n, int64_t* first_index_out_h, void* stream);
+int pomp_nn_add_h(pomp_nn* h, const double* pts_h, int64_t n, int64_t* first_index_out_h);
+/* NearestNeighbors.set (:65-74): bulk replace + index rebuild */
+int pomp_nn_set(pomp_nn* h, const double* pts, int64_t n, void* stream);
+int pomp_nn_set_h(pomp_nn* h, const double* pts_h, int64_t n);
+/* NearestNeighbors.remove (:41-62): tombstone by insertion index (the host binding resolves
+   (point,data) -> index, exactly-equal-coordinates semantics stay on the host) */
+int pomp_nn_remove(pomp_nn* h, int64_t index);
+/* filter-as-mask: reject_mask_h[i] != 0 means the reference's filter(point,data) returned True.
+   NULL clears the mask.  n must equal pomp_nn_size(). */
+int pomp_nn_set_mask_h(pomp_nn* h, const uint8_t* reject_mask_h, int64_t n);
+/* CostSpaceRRT.updateBestCost mutates the metric in place (kinodynamicplanner.py:1059-1077) */
+int pomp_nn_update_metric(pomp_nn* h, const pomp_metric_desc* metric);
+int64_t pomp_nn_size(const pomp_nn* h);
+/* tuning knobs: "grid_min_points" (below: brute force), "points_per_cell", "sort_queries" */
+int pomp_nn_set_param(pomp_nn* h, const char* name, double value);
+/* (re)build the uniform-grid bucket index over all points now (otherwise built lazily) */
+int pomp_nn_build_index(pomp_nn* h, void* stream);
+
+/* NearestNeighbors.nearest (:76-96): idx = -1 and dist = +inf when no admissible point exists */
+int pomp_nn_nearest(pomp_nn* h, const double* q, int64_t nq, int64_t* idx, double* dist, void* stream);
+int pomp_nn_nearest_h(pomp_nn* h, const double* q_h, int64_t nq, int64_t* idx_h, double* dist_h);
+/* NearestNeighbors.knearest (:98-116) + KNearestResult (knn.py:7-30): per query the k smallest
+   (dist, idx) ascending; unused slots are idx=-1, dist=+inf; count[q] = number found */
+int pomp_nn_knearest(pomp_nn* h, const double* q, int64_t nq, int32_t k, int64_t* idx, double* dist,
+                     int32_t* count, void* stream);
+int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32_t k, int64_t* idx_h,
+                       double* dist_h, int32_t* count_h);
+/* NearestNeighbors.neighbors (:118-141).  inclusive=1: d <= radius (kd-tree branch, kdtree.py:347),
+   inclusive=0: d < radius (brute-force branch :139).  CSR output: offsets[nq+1], idx sorted ascending
+   per query.  If the hits do not fit idx_capacity the call fills only offsets and *needed_h and
+   returns POMP_ERR_CAPACITY. */
+int pomp_nn_neighbors(pomp_nn* h, const double* q, int64_t nq, double radius, int inclusive,
+                      int64_t* offsets, int64_t* idx, int64_t idx_capacity, int64_t* needed_h,
+                      void* stream);
+int pomp_nn_neighbors_h(pomp_nn* h, const double* q_h, int64_t nq, double radius, int inclusive,
+                        int64_t* offsets_h, int64_t* idx_h, int64_t idx_capacity, int64_t* needed_h);
+
+/* multi-GPU: merge G per-shard candidate lists [G][nq][k] (already carrying GLOBAL
+   indices) into the k best per query by (dist, idx).  The exchange itself (NCCL all-to-all /
+   all-gather over NVLink) is issued by the host binding through torch.distributed. */
+int pomp_nn_merge_candidates(const int64_t* idx_in, const double* dist_in, int32_t n_shards, int64_t nq,
+                             int32_t k, int64_t* idx_out, double* dist_out, int32_t* count_out,
+                             void* stream);
+
+/* ---------------------------------------------------------------- feasibility ---------- */
+/* ConfigurationSpace.feasible for box-bounded product spaces with 2-D box / disc obstacles:
+   BoxSet.contains (sets.py:177-182), Geometric2DCSpace.feasible (geometric.py:56-60),
+   Circle.contains (:15-16), MultiConfigurationSpace.feasible (configurationspace.py:196-199). */
+typedef struct {
+  int32_t dim;
+  int32_t obstacle_dim0;      /* the two coordinates the 2-D obstacles live in */
+  int32_t obstacle_dim1;
+  int32_t n_boxes;
+  int32_t n_circles;
+  int32_t _pad;
+  double lo[POMP_MAX_DIM];    /* -inf / +inf for coordinates without a bound check */
+  double hi[POMP_MAX_DIM];
+  const double* boxes_h;      /* n_boxes x 4: xmin, ymin, xmax, ymax (closed)  */
+  const double* circles_h;    /* n_circles x 3: cx, cy, r (closed disc)        */
+} pomp_space_desc;
+
+typedef struct pomp_space pomp_space;
+int pomp_space_create(const pomp_space_desc* desc, int device, pomp_space** out);
+int pomp_space_destroy(pomp_space* s);
+/* CostControlSpace.setCostMax / in-place bound updates (costspace.py:26-30) */
+int pomp_space_set_bounds(pomp_space* s, const double* lo_h, const double* hi_h);
+
+int pomp_feasible(pomp_space* s, const double* x, int64_t n, uint8_t* ok, void* stream);
+int pomp_feasible_h(pomp_space* s, const double* x_h, int64_t n, uint8_t* ok_h);
+
+/* ---------------------------------------------------------------- edge checks ---------- */
+/* EpsilonEdgeChecker.feasible (edgechecker.py:20-30) on LinearInterpolator edges
+   (interpolators.py:28-35): a, b are n x dim. */
+int pomp_edge_check(pomp_space* s, const double* a, const double* b, int64_t n, double resolution,
+                    uint8_t* ok, void* stream);
+int pomp_edge_check_h(pomp_space* s, const double* a_h, const double* b_h, int64_t n, double resolution,
+                      uint8_t* ok_h);
+/* same, edges given as index pairs ij[n_edges][2] into a roadmap node array nodes[*][dim] */
+int pomp_edge_check_indexed(pomp_space* s, const double* nodes, const int32_t* ij, int64_t n_edges,
+                            double resolution, uint8_t* ok, void* stream);
+/* PiecewiseLinearInterpolator / GeodesicInterpolator edges (interpolators.py:37-48,73-102):
+   path p has waypoints [path_offsets[p], path_offsets[p+1]) of `waypoints` (row-major x dim);
+   length / interpolation follow `geodesic` (EUCLIDEAN or GEODESIC_PRODUCT). */
+int pomp_edge_check_path(pomp_space* s, const pomp_metric_desc* geodesic, const double* waypoints,
+                         const int32_t* path_offsets, int64_t n_paths, double resolution, uint8_t* ok,
+                         void* stream);
+int pomp_edge_check_path_h(pomp_space* s, const pomp_metric_desc* geodesic, const double* waypoints_h,
+                           const int32_t* path_offsets_h, int64_t n_paths, double resolution,
+                           uint8_t* ok_h);
+
+/* ---------------------------------------------------------------- propagation ---------- */
+typedef enum {
+  POMP_DYN_ADAPTOR = 0,    /* ControlSpaceAdaptor.nextState: x' = u           (controlspace.py:78-79) */
+  POMP_DYN_CV = 1,         /* CVControlSpace.nextState closed form            (statespace.py:62-70)   */
+  POMP_DYN_CV_EULER = 2,   /* CVControlSpace.trajectory()[-1] stepwise        (statespace.py:47-61)   */
+  POMP_DYN_DUBINS = 3,     /* DubinsCarSpace.nextState                        (dubins.py:107-125)     */
+  POMP_DYN_PENDULUM = 4,   /* LambdaKinodynamicSpace Euler + Pendulum.derivative (controlspace.py:249-267, pendulum.py:152-154) */
+  POMP_DYN_LTI = 5,        /* LTIControlSpace: A x + B u                      (controlspace.py:101-102) */
+  POMP_DYN_FLAPPY = 6      /* FlappyControlSpace.eval(x,u,1)                  (flappy.py:20-31)        */
+} pomp_dyn_kind;
+
+typedef enum {
+  POMP_COST_NONE = 0,       /* plain ControlSpace                                                     */
+  POMP_COST_TIME = 1,       /* CostControlSpace + TimeObjectiveFunction: c += u[0]       (objectives.py) */
+  POMP_COST_ABS_U0 = 2,     /* DubinsCarDistanceObjectiveFunction(1): c += |u[0]|       (dubins.py:131-135) */
+  POMP_COST_PATH_LENGTH = 3 /* PathLengthObjectiveFunction on an adaptor: c += euclid(x,u)             */
+} pomp_cost_kind;
+
+typedef struct {
+  int32_t kind;      /* pomp_dyn_kind */
+  int32_t x_dim;     /* base state dimension (without cost coordinate) */
+  int32_t u_dim;     /* control dimension (u[0] = duration for the integrated kinds) */
+  int32_t cost_kind; /* pomp_cost_kind: when != NONE states carry a trailing cost coordinate (costspace.py:35-38) */
+  double dt;         /* integration step (KinodynamicSpace.dt) */
+  double p[8];       /* PENDULUM: g, m, L ; FLAPPY: v_x, gravity, thrust */
+  double A[POMP_MAX_DIM * POMP_MAX_DIM]; /* LTI, row-major x_dim x x_dim */
+  double B[POMP_MAX_DIM * POMP_MAX_DIM]; /* LTI, row-major x_dim x u_dim */
+} pomp_dyn_desc;
+
+/* ControlSpace.nextState for n (x,u) pairs; x: n x X, u: n x u_dim, xnext: n x X with
+   X = x_dim (+1 with a cost objective). */
+int pomp_next_state(const pomp_dyn_desc* dyn, const double* x, const double* u, int64_t n, double* xnext,
+                    void* stream);
+int pomp_next_state_h(const pomp_dyn_desc* dyn, const double* x_h, const double* u_h, int64_t n,
+                      double* xnext_h);
+/* RandomControlSelector.select (kinodynamicplanner.py:66-84), fused nextState + metric + strict-<
+   arg-min (first minimum wins): for each of B parents, S candidate controls u[B][S][u_dim];
+   valid[B][S] = U.contains(u).  best[b] = -1 when no valid candidate has finite distance. */
+int pomp_select_control(const pomp_dyn_desc* dyn, const pomp_metric_desc* metric, const double* x,
+                        const double* xdes, const double* u, const uint8_t* valid, int64_t B, int32_t S,
+                        int32_t* best, double* xnext_best, double* dist_best, void* stream);
+int pomp_select_control_h(const pomp_dyn_desc* dyn, const pomp_metric_desc* metric, const double* x_h,
+                          const double* xdes_h, const double* u_h, const uint8_t* valid_h, int64_t B,
+                          int32_t S, int32_t* best_h, double* xnext_best_h, double* dist_best_h);
+
+/* EpsilonEdgeChecker.feasible on controlSpace.interpolator(x,u) without materialising the curve on
+   the host: ADAPTOR -> LinearInterpolator(x,u); DUBINS -> DubinsCarInterpolator (dubins.py:62-73:
+   length |u0|, eval(s) = nextState(x,[u0*s,u1])); PENDULUM / CV_EULER ->
+   PiecewiseLinearInterpolator(trajectory(x,u)) under `geodesic` (controlspace.py:149-172,249-271).
+   x: n x x_dim BASE states (CostEdgeChecker checks components[0], kinodynamicplanner.py:895-896). */
+int pomp_edge_check_control(pomp_space* s, const pomp_dyn_desc* dyn, const pomp_metric_desc* geodesic,
+                            const double* x, const double* u, int64_t n, double resolution, uint8_t* ok,
+                            void* stream);
+int pomp_edge_check_control_h(pomp_space* s, const pomp_dyn_desc* dyn, const pomp_metric_desc* geodesic,
+                              const double* x_h, const double* u_h, int64_t n, double resolution,
+                              uint8_t* ok_h);
+
+/* ---------------------------------------------------------------- fused RRT extend ------ */
+/* One kinematic RRT.expand step (kinodynamicplanner.py:354-411 with KinematicControlSelector
+   :95-100, LinearInterpolator, EpsilonEdgeChecker) in ONE launch: nearest(xrand) -> steer to at most
+   max_step -> sampled edge check -> append on success.  Host supplies the already drawn, already
+   point-feasible xrand.  Outputs (host): parent index (-1: none), the new point (dim doubles) and
+   whether it was added.  The metric of `h` must be EUCLIDEAN. */
+int pomp_rrt_extend_h(pomp_nn* h, pomp_space* s, const double* xrand_h, double max_step, double resolution,
+                      int64_t* parent_h, double* xnew_h, int32_t* added_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POMP_B200_H */
