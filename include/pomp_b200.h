@@ -247,12 +247,16 @@ int pomp_edge_check_control_h(pomp_space* s, const pomp_dyn_desc* dyn, const pom
 
 /* ---------------------------------------------------------------- fused RRT extend ------ */
 /* One kinematic RRT.expand step (kinodynamicplanner.py:354-411 with KinematicControlSelector
-   :95-100, LinearInterpolator, EpsilonEdgeChecker) in ONE launch: nearest(xrand) -> steer to at most
-   max_step -> sampled edge check -> append on success.  Host supplies the already drawn, already
-   point-feasible xrand.  Outputs (host): parent index (-1: none), the new point (dim doubles) and
-   whether it was added.  The metric of `h` must be EUCLIDEAN. */
-int pomp_rrt_extend_h(pomp_nn* h, pomp_space* s, const double* xrand_h, double max_step, double resolution,
-                      int64_t* parent_h, double* xnew_h, int32_t* added_h);
+   :95-100, LinearInterpolator, EpsilonEdgeChecker) in ONE launch: [feasible(xrand)] ->
+   nearest(xrand) -> steer to at most max_step -> sampled edge check -> append to the index on success.
+   The host supplies the already drawn xrand (Python's RNG stays on the host); check_sample != 0
+   also runs RRT.expand's cspace.feasible(xrand) test (:362) on the device.
+   Outputs (host): parent index (-1: no admissible node, -2: xrand infeasible), the new point
+   (dim doubles), the edge length |parent - xnew| (PathLengthObjectiveFunction.incremental) and
+   whether the node was appended.  The metric of `h` must be EUCLIDEAN. */
+int pomp_rrt_extend_h(pomp_nn* h, pomp_space* s, const double* xrand_h, int check_sample, double max_step,
+                      double resolution, int64_t* parent_h, double* xnew_h, double* edge_len_h,
+                      int32_t* added_h);
 
 #ifdef __cplusplus
 }

@@ -101,7 +101,7 @@ SIGNATURES = {
     "pomp_next_state_h": (C.c_int, [_DD, _P, _P, _I64, _P]),
     "pomp_select_control": (C.c_int, [_DD, _MD, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P]),
     "pomp_select_control_h": (C.c_int, [_DD, _MD, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
-    "pomp_rrt_extend_h": (C.c_int, [_P, _P, _P, _D, _D, _P, _P, _P]),
+    "pomp_rrt_extend_h": (C.c_int, [_P, _P, _P, C.c_int, _D, _D, _P, _P, _P, _P]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpomp_b200.so")

@@ -1,0 +1,321 @@
+"""Thin object layer over the C-ABI (csrc/libpomp_b200.so): owns handles, marshals numpy/torch
+buffers into plain pointers.  This is the ONLY compute backend of the product -- every method
+ends in a CUDA kernel launch; without the library or a device it raises.
+
+(The classes here define the small internal interface that the host-side drop-ins use; the CPU
+test-suite substitutes an oracle-backed fake with the same methods to exercise the host logic of
+the drop-ins where no GPU exists.  That fake lives under tests/, never here.)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import check
+
+
+def _f64(a, cols=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _is_torch_cuda(t):
+    return hasattr(t, "is_cuda") and t.is_cuda
+
+
+class CudaNN(object):
+    """NearestNeighbors state on one GPU (pomp_nn_* entry points)."""
+
+    def __init__(self, metric_spec, device=0, capacity_hint=0):
+        self.lib = _abi.load_library()
+        self.spec = metric_spec
+        self.dim = metric_spec.dim
+        self.device = device
+        self._h = C.c_void_p()
+        check(self.lib, self.lib.pomp_nn_create(C.byref(metric_spec.desc()), capacity_hint, device, C.byref(self._h)))
+        # reusable single-query buffers
+        self._q1 = (C.c_double * self.dim)()
+        self._i1 = C.c_int64()
+        self._d1 = C.c_double()
+        self._first = C.c_int64()
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self.lib.pomp_nn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mutation
+    def reset(self):
+        check(self.lib, self.lib.pomp_nn_reset(self._h))
+
+    def size(self):
+        return self.lib.pomp_nn_size(self._h)
+
+    def add(self, pts):
+        pts = _f64(pts, self.dim)
+        check(self.lib, self.lib.pomp_nn_add_h(self._h, _ptr(pts), len(pts), C.byref(self._first)))
+        return self._first.value
+
+    def add_one(self, pt):
+        q = self._q1
+        for j in range(self.dim):
+            q[j] = pt[j]
+        check(self.lib, self.lib.pomp_nn_add_h(self._h, q, 1, C.byref(self._first)))
+        return self._first.value
+
+    def set(self, pts):
+        pts = _f64(pts, self.dim)
+        check(self.lib, self.lib.pomp_nn_set_h(self._h, _ptr(pts), len(pts)))
+
+    def set_device(self, ptr, n, stream=None):
+        check(self.lib, self.lib.pomp_nn_set(self._h, C.c_void_p(ptr), n, C.c_void_p(stream or 0)))
+
+    def remove(self, index):
+        check(self.lib, self.lib.pomp_nn_remove(self._h, index))
+
+    def set_mask(self, mask):
+        if mask is None:
+            check(self.lib, self.lib.pomp_nn_set_mask_h(self._h, None, 0))
+        else:
+            m = np.ascontiguousarray(np.asarray(mask, dtype=np.uint8))
+            check(self.lib, self.lib.pomp_nn_set_mask_h(self._h, _ptr(m), len(m)))
+
+    def update_metric(self, metric_spec):
+        self.spec = metric_spec
+        check(self.lib, self.lib.pomp_nn_update_metric(self._h, C.byref(metric_spec.desc())))
+
+    def set_param(self, name, value):
+        check(self.lib, self.lib.pomp_nn_set_param(self._h, name.encode(), float(value)))
+
+    def build_index(self, stream=None):
+        check(self.lib, self.lib.pomp_nn_build_index(self._h, C.c_void_p(stream or 0)))
+
+    # ---- queries, host buffers
+    def nearest_one(self, pt):
+        q = self._q1
+        for j in range(self.dim):
+            q[j] = pt[j]
+        check(self.lib, self.lib.pomp_nn_nearest_h(self._h, q, 1, C.byref(self._i1), C.byref(self._d1)))
+        return self._i1.value, self._d1.value
+
+    def nearest(self, q):
+        q = _f64(q, self.dim)
+        idx = np.empty(len(q), np.int64)
+        dist = np.empty(len(q), np.float64)
+        check(self.lib, self.lib.pomp_nn_nearest_h(self._h, _ptr(q), len(q), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def knearest(self, q, k):
+        q = _f64(q, self.dim)
+        idx = np.empty((len(q), k), np.int64)
+        dist = np.empty((len(q), k), np.float64)
+        cnt = np.empty(len(q), np.int32)
+        check(self.lib, self.lib.pomp_nn_knearest_h(self._h, _ptr(q), len(q), k, _ptr(idx), _ptr(dist), _ptr(cnt)))
+        return idx, dist, cnt
+
+    def neighbors(self, q, radius, inclusive=True):
+        q = _f64(q, self.dim)
+        off = np.empty(len(q) + 1, np.int64)
+        cap = max(64, 32 * len(q))
+        need = C.c_int64()
+        while True:
+            idx = np.empty(cap, np.int64)
+            rc = self.lib.pomp_nn_neighbors_h(self._h, _ptr(q), len(q), float(radius), 1 if inclusive else 0,
+                                              _ptr(off), _ptr(idx), cap, C.byref(need))
+            if rc == _abi.POMP_ERR_CAPACITY:
+                cap = int(need.value)
+                continue
+            check(self.lib, rc)
+            return off, idx[:need.value]
+
+    # ---- queries, device buffers (raw pointers: torch tensors' data_ptr())
+    def nearest_device(self, q_ptr, nq, idx_ptr, dist_ptr, stream=None):
+        check(self.lib, self.lib.pomp_nn_nearest(self._h, C.c_void_p(q_ptr), nq, C.c_void_p(idx_ptr),
+                                                 C.c_void_p(dist_ptr), C.c_void_p(stream or 0)))
+
+    def knearest_device(self, q_ptr, nq, k, idx_ptr, dist_ptr, cnt_ptr=None, stream=None):
+        check(self.lib, self.lib.pomp_nn_knearest(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(idx_ptr),
+                                                  C.c_void_p(dist_ptr), C.c_void_p(cnt_ptr or 0),
+                                                  C.c_void_p(stream or 0)))
+
+    def neighbors_device(self, q_ptr, nq, radius, inclusive, off_ptr, idx_ptr, idx_capacity, stream=None):
+        need = C.c_int64()
+        rc = self.lib.pomp_nn_neighbors(self._h, C.c_void_p(q_ptr), nq, float(radius), 1 if inclusive else 0,
+                                        C.c_void_p(off_ptr), C.c_void_p(idx_ptr), idx_capacity, C.byref(need),
+                                        C.c_void_p(stream or 0))
+        if rc != _abi.POMP_ERR_CAPACITY:
+            check(self.lib, rc)
+        return rc, need.value
+
+
+def merge_candidates_device(idx_in_ptr, dist_in_ptr, n_shards, nq, k, idx_out_ptr, dist_out_ptr, cnt_out_ptr=None,
+                            stream=None):
+    lib = _abi.load_library()
+    check(lib, lib.pomp_nn_merge_candidates(C.c_void_p(idx_in_ptr), C.c_void_p(dist_in_ptr), n_shards, nq, k,
+                                            C.c_void_p(idx_out_ptr), C.c_void_p(dist_out_ptr),
+                                            C.c_void_p(cnt_out_ptr or 0), C.c_void_p(stream or 0)))
+
+
+class CudaSpace(object):
+    """Feasibility + edge checks on one GPU (pomp_space_*, pomp_feasible*, pomp_edge_check*)."""
+
+    def __init__(self, space_spec, device=0):
+        self.lib = _abi.load_library()
+        self.spec = space_spec
+        self.dim = space_spec.dim
+        self.device = device
+        self._h = C.c_void_p()
+        d = space_spec.desc()
+        check(self.lib, self.lib.pomp_space_create(C.byref(d), device, C.byref(self._h)))
+        self._a1 = (C.c_double * _abi.MAX_DIM)()
+        self._b1 = (C.c_double * _abi.MAX_DIM)()
+        self._ok1 = C.c_uint8()
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self.lib.pomp_space_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_bounds(self, lo, hi):
+        lo, hi = _f64(lo), _f64(hi)
+        check(self.lib, self.lib.pomp_space_set_bounds(self._h, _ptr(lo), _ptr(hi)))
+
+    def feasible(self, x):
+        x = _f64(x, self.dim)
+        ok = np.empty(len(x), np.uint8)
+        check(self.lib, self.lib.pomp_feasible_h(self._h, _ptr(x), len(x), _ptr(ok)))
+        return ok.astype(bool)
+
+    def feasible_one(self, x):
+        a = self._a1
+        for j in range(self.dim):
+            a[j] = x[j]
+        check(self.lib, self.lib.pomp_feasible_h(self._h, a, 1, C.byref(self._ok1)))
+        return bool(self._ok1.value)
+
+    def edge_check(self, a, b, resolution):
+        a, b = _f64(a, self.dim), _f64(b, self.dim)
+        ok = np.empty(len(a), np.uint8)
+        check(self.lib, self.lib.pomp_edge_check_h(self._h, _ptr(a), _ptr(b), len(a), float(resolution), _ptr(ok)))
+        return ok.astype(bool)
+
+    def edge_check_one(self, a, b, resolution):
+        pa, pb = self._a1, self._b1
+        for j in range(self.dim):
+            pa[j] = a[j]
+            pb[j] = b[j]
+        check(self.lib, self.lib.pomp_edge_check_h(self._h, pa, pb, 1, float(resolution), C.byref(self._ok1)))
+        return bool(self._ok1.value)
+
+    def edge_check_path(self, geodesic_spec, waypoints, offsets, resolution):
+        wp = _f64(waypoints, self.dim)
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32))
+        ok = np.empty(len(off) - 1, np.uint8)
+        check(self.lib, self.lib.pomp_edge_check_path_h(self._h, C.byref(geodesic_spec.desc()), _ptr(wp), _ptr(off),
+                                                        len(off) - 1, float(resolution), _ptr(ok)))
+        return ok.astype(bool)
+
+    def edge_check_control(self, dyn_spec, geodesic_spec, x, u, resolution):
+        x, u = _f64(x, dyn_spec.x_dim), _f64(u, dyn_spec.u_dim)
+        ok = np.empty(len(x), np.uint8)
+        g = C.byref(geodesic_spec.desc()) if geodesic_spec is not None else None
+        check(self.lib, self.lib.pomp_edge_check_control_h(self._h, C.byref(dyn_spec.desc()), g, _ptr(x), _ptr(u),
+                                                           len(x), float(resolution), _ptr(ok)))
+        return ok.astype(bool)
+
+    # device-pointer variants
+    def feasible_device(self, x_ptr, n, ok_ptr, stream=None):
+        check(self.lib, self.lib.pomp_feasible(self._h, C.c_void_p(x_ptr), n, C.c_void_p(ok_ptr),
+                                               C.c_void_p(stream or 0)))
+
+    def edge_check_device(self, a_ptr, b_ptr, n, resolution, ok_ptr, stream=None):
+        check(self.lib, self.lib.pomp_edge_check(self._h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), n, float(resolution),
+                                                 C.c_void_p(ok_ptr), C.c_void_p(stream or 0)))
+
+    def edge_check_indexed_device(self, nodes_ptr, ij_ptr, n_edges, resolution, ok_ptr, stream=None):
+        check(self.lib, self.lib.pomp_edge_check_indexed(self._h, C.c_void_p(nodes_ptr), C.c_void_p(ij_ptr), n_edges,
+                                                         float(resolution), C.c_void_p(ok_ptr),
+                                                         C.c_void_p(stream or 0)))
+
+
+class CudaDynamics(object):
+    """Batched nextState / fused control selection (pomp_next_state*, pomp_select_control*)."""
+
+    def __init__(self, dyn_spec):
+        self.lib = _abi.load_library()
+        self.spec = dyn_spec
+        self._desc = dyn_spec.desc()
+
+    def next_state(self, x, u):
+        X = self.spec.state_dim()
+        x, u = _f64(x, X), _f64(u, self.spec.u_dim)
+        out = np.empty_like(x)
+        check(self.lib, self.lib.pomp_next_state_h(C.byref(self._desc), _ptr(x), _ptr(u), len(x), _ptr(out)))
+        return out
+
+    def select_control(self, metric_spec, x, xdes, u, valid=None):
+        X = self.spec.state_dim()
+        x, xdes = _f64(x, X), _f64(xdes, X)
+        B = len(x)
+        u = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(B, -1, self.spec.u_dim))
+        S = u.shape[1]
+        v = None if valid is None else np.ascontiguousarray(np.asarray(valid, dtype=np.uint8).reshape(B, S))
+        best = np.empty(B, np.int32)
+        xb = np.empty((B, X), np.float64)
+        db = np.empty(B, np.float64)
+        check(self.lib, self.lib.pomp_select_control_h(C.byref(self._desc), C.byref(metric_spec.desc()), _ptr(x),
+                                                       _ptr(xdes), _ptr(u), _ptr(v) if v is not None else None, B, S,
+                                                       _ptr(best), _ptr(xb), _ptr(db)))
+        return best, xb, db
+
+    def next_state_device(self, x_ptr, u_ptr, n, out_ptr, stream=None):
+        check(self.lib, self.lib.pomp_next_state(C.byref(self._desc), C.c_void_p(x_ptr), C.c_void_p(u_ptr), n,
+                                                 C.c_void_p(out_ptr), C.c_void_p(stream or 0)))
+
+    def select_control_device(self, metric_spec, x_ptr, xdes_ptr, u_ptr, valid_ptr, B, S, best_ptr, xbest_ptr,
+                              dbest_ptr, stream=None):
+        check(self.lib, self.lib.pomp_select_control(C.byref(self._desc), C.byref(metric_spec.desc()),
+                                                     C.c_void_p(x_ptr), C.c_void_p(xdes_ptr), C.c_void_p(u_ptr),
+                                                     C.c_void_p(valid_ptr or 0), B, S, C.c_void_p(best_ptr),
+                                                     C.c_void_p(xbest_ptr), C.c_void_p(dbest_ptr),
+                                                     C.c_void_p(stream or 0)))
+
+
+def rrt_extend(nn, space, xrand, max_step, resolution, check_sample=True, _buf={}):
+    """pomp_rrt_extend_h: returns (parent_index, xnew list, edge_length, added)."""
+    lib = nn.lib
+    D = nn.dim
+    if D not in _buf:
+        _buf[D] = ((C.c_double * D)(), (C.c_double * D)(), C.c_int64(), C.c_int32(), C.c_double())
+    q, xn, parent, added, elen = _buf[D]
+    for j in range(D):
+        q[j] = xrand[j]
+    check(lib, lib.pomp_rrt_extend_h(nn._h, space._h, q, 1 if check_sample else 0, float(max_step),
+                                     float(resolution), C.byref(parent), xn, C.byref(elen), C.byref(added)))
+    return parent.value, list(xn), elen.value, bool(added.value)
+
+
+def launch_count():
+    return _abi.load_library().pomp_launch_count()
+
+
+def device_count():
+    return _abi.load_library().pomp_device_count()

@@ -1,0 +1,1277 @@
+// nn.cu -- NearestNeighbors on the device (pomp/structures/nearestneighbors.py:13-141).
+//
+// Two exact search regimes over the same insertion-ordered fp64 AoS point store:
+//   * brute force, warp per (query, point-chunk): any metric, any k; used while the node set or
+//     the query batch is small (planner-in-the-loop calls, N <= ~1e5) -- FP64-ALU bound;
+//   * uniform-grid bucket index (grid.cuh), thread per query: large node sets and query batches
+//     (the 16 Mi point / 1 Mi query configuration) -- HBM/L2 bound.
+// Both order candidates by (distance, insertion index), so they agree with each other and with
+// the reference's brute-force scan bit for bit.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "grid.cuh"
+#include "nn_handle.cuh"
+#include "scan.cuh"
+#include "topk.cuh"
+
+using namespace pomp;
+
+static int base_dim(const pomp_metric_desc& m) { return m.has_cost ? m.dim - 1 : m.dim; }
+
+int pomp::validate_metric(const pomp_metric_desc* m) {
+  POMP_REQUIRE(m != nullptr, "metric descriptor is NULL");
+  POMP_REQUIRE(m->dim >= 1 && m->dim <= POMP_MAX_DIM, "metric dim %d outside 1..%d", m->dim, POMP_MAX_DIM);
+  POMP_REQUIRE(m->kind >= 0 && m->kind <= POMP_METRIC_GEODESIC_PRODUCT, "unknown metric kind %d", m->kind);
+  POMP_REQUIRE(!m->has_cost || m->dim >= 2, "cost metric needs at least one base coordinate");
+  if (m->kind == POMP_METRIC_GEODESIC_PRODUCT) {
+    POMP_REQUIRE(m->n_comp >= 1 && m->n_comp <= POMP_MAX_COMP, "bad component count %d", m->n_comp);
+    int s = 0;
+    for (int c = 0; c < m->n_comp; c++) {
+      POMP_REQUIRE(m->comp_dim[c] >= 1, "component %d has dimension %d", c, m->comp_dim[c]);
+      POMP_REQUIRE(m->comp_kind[c] != POMP_COMP_SO2 || m->comp_dim[c] == 1, "SO2 component must have dim 1");
+      s += m->comp_dim[c];
+    }
+    POMP_REQUIRE(s == base_dim(*m), "component dims sum to %d, expected %d", s, base_dim(*m));
+  }
+  return POMP_OK;
+}
+
+int pomp::nn_grow(pomp_nn* h, int64_t need, cudaStream_t st) {
+  if (need <= h->cap) return POMP_OK;
+  int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(1024, h->cap * 2));
+  double* np = nullptr;
+  uint8_t* ns = nullptr;
+  cudaError_t e = cudaMalloc((void**)&np, sizeof(double) * (size_t)ncap * h->D);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ns, (size_t)ncap);
+  if (e != cudaSuccess) {
+    if (np) cudaFree(np);
+    set_error("cudaMalloc for %lld points failed: %s", (long long)ncap, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? POMP_ERR_NOMEM : POMP_ERR_CUDA;
+  }
+  CUDA_TRY(cudaMemsetAsync(ns, 0, (size_t)ncap, st));
+  if (h->n_dev > 0) {
+    CUDA_TRY(cudaMemcpyAsync(np, h->d_pts, sizeof(double) * (size_t)h->n_dev * h->D, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ns, h->d_skip, (size_t)h->n_dev, cudaMemcpyDeviceToDevice, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h->d_pts) cudaFree(h->d_pts);
+  if (h->d_skip) cudaFree(h->d_skip);
+  h->d_pts = np;
+  h->d_skip = ns;
+  h->cap = ncap;
+  return POMP_OK;
+}
+
+// upload host-side pending adds
+int pomp::nn_flush(pomp_nn* h, cudaStream_t st) {
+  if (h->pending.empty()) return POMP_OK;
+  int64_t m = (int64_t)h->pending.size() / h->D;
+  POMP_TRY(nn_grow(h, h->n_dev + m, st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts + h->n_dev * h->D, h->pending.data(), sizeof(double) * h->pending.size(),
+                           cudaMemcpyHostToDevice, st));
+  h->n_dev += m;
+  h->pending.clear();
+  return POMP_OK;
+}
+
+// ============================================================================ brute force kernels
+// One warp per (query, split).  Lanes stride over the split's points.
+
+__device__ __forceinline__ void load_q(const double* q, int D, double* out) {
+  for (int j = 0; j < D; j++) out[j] = q[j];
+}
+
+struct SplitGeom {
+  int nsplit;
+  long long chunk;
+};
+
+__global__ void bf_nearest_kernel(const double* __restrict__ pts, long long n, pomp_metric_desc m,
+                                  const uint8_t* __restrict__ skip, const double* __restrict__ q, long long nq,
+                                  SplitGeom sg, double* __restrict__ part_d, int* __restrict__ part_i) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= nq * sg.nsplit) return;
+  long long qi = warp / sg.nsplit;
+  int sp = (int)(warp % sg.nsplit);
+  const int D = m.dim;
+  double qq[POMP_MAX_DIM], p[POMP_MAX_DIM];
+  load_q(q + qi * D, D, qq);
+  long long b = (long long)sp * sg.chunk, e = min(n, b + sg.chunk);
+  double bd = POMP_INF;
+  int bi = IDX_NONE;
+  const bool euclid = (m.kind == POMP_METRIC_EUCLIDEAN && !m.has_cost);
+  for (long long i = b + lane; i < e; i += 32) {
+    if (skip && skip[i]) continue;
+    for (int j = 0; j < D; j++) p[j] = __ldg(pts + i * D + j);
+    double d;
+    if (euclid) {
+      double s = 0.0;
+      for (int j = 0; j < D; j++) {
+        double t = p[j] - qq[j];
+        s = s + t * t;
+      }
+      d = sqrt(s);
+    } else {
+      d = metric_eval(m, p, qq);
+    }
+    if (d < bd) {  // strict '<' in ascending index order keeps the first minimum (nearestneighbors.py:93)
+      bd = d;
+      bi = (int)i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double od = __shfl_xor_sync(FULL_MASK, bd, o);
+    int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+    if (key_less(od, oi, bd, bi)) {
+      bd = od;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    part_d[warp] = bd;
+    part_i[warp] = bi;
+  }
+}
+
+__global__ void bf_nearest_reduce_kernel(const double* __restrict__ part_d, const int* __restrict__ part_i,
+                                         long long nq, int nsplit, int64_t* __restrict__ idx,
+                                         double* __restrict__ dist) {
+  long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  double bd = POMP_INF;
+  int bi = IDX_NONE;
+  for (int s = 0; s < nsplit; s++) {
+    double d = part_d[qi * nsplit + s];
+    int i = part_i[qi * nsplit + s];
+    if (key_less(d, i, bd, bi)) {
+      bd = d;
+      bi = i;
+    }
+  }
+  bool found = bd < POMP_INF;
+  idx[qi] = found ? (int64_t)bi : -1;
+  dist[qi] = found ? bd : POMP_INF;
+}
+
+// Single query passed by value, result written straight into a mapped host mailbox by the last
+// block to finish: one launch + one stream sync per planner-side nearest() call.
+__global__ void bf_single_nearest_kernel(const double* __restrict__ pts, long long n, pomp_metric_desc m,
+                                         const uint8_t* __restrict__ skip, QueryArg qa, double* part_d,
+                                         int* part_i, unsigned int* ticket, Mailbox* out) {
+  const int D = m.dim;
+  double p[POMP_MAX_DIM];
+  double bd = POMP_INF;
+  int bi = IDX_NONE;
+  const bool euclid = (m.kind == POMP_METRIC_EUCLIDEAN && !m.has_cost);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (skip && skip[i]) continue;
+    for (int j = 0; j < D; j++) p[j] = __ldg(pts + i * D + j);
+    double d;
+    if (euclid) {
+      double s = 0.0;
+      for (int j = 0; j < D; j++) {
+        double t = p[j] - qa.v[j];
+        s = s + t * t;
+      }
+      d = sqrt(s);
+    } else {
+      d = metric_eval(m, p, qa.v);
+    }
+    if (key_less(d, (int)i, bd, bi)) {
+      bd = d;
+      bi = (int)i;
+    }
+  }
+  __shared__ double sd[32];
+  __shared__ int si[32];
+  __shared__ bool last;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double od = __shfl_xor_sync(FULL_MASK, bd, o);
+    int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+    if (key_less(od, oi, bd, bi)) {
+      bd = od;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    sd[w] = bd;
+    si[w] = bi;
+  }
+  __syncthreads();
+  if (w == 0) {
+    bd = lane < nw ? sd[lane] : POMP_INF;
+    bi = lane < nw ? si[lane] : IDX_NONE;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double od = __shfl_xor_sync(FULL_MASK, bd, o);
+      int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+      if (key_less(od, oi, bd, bi)) {
+        bd = od;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      part_d[blockIdx.x] = bd;
+      part_i[blockIdx.x] = bi;
+      __threadfence();
+      unsigned int t = atomicAdd(ticket, 1u);
+      last = (t == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  bd = POMP_INF;
+  bi = IDX_NONE;
+  for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    double d = ((volatile double*)part_d)[b];
+    int i = ((volatile int*)part_i)[b];
+    if (key_less(d, i, bd, bi)) {
+      bd = d;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double od = __shfl_xor_sync(FULL_MASK, bd, o);
+    int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+    if (key_less(od, oi, bd, bi)) {
+      bd = od;
+      bi = oi;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+    sd[w] = bd;
+    si[w] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int x = 1; x < nw; x++)
+      if (key_less(sd[x], si[x], bd, bi)) {
+        bd = sd[x];
+        bi = si[x];
+      }
+    bool found = bd < POMP_INF;
+    out->idx = found ? (int64_t)bi : -1;
+    out->dist = found ? bd : POMP_INF;
+    *ticket = 0;  // re-arm for the next call
+    __threadfence_system();
+  }
+}
+
+template <int KL>
+__global__ void bf_knn_kernel(const double* __restrict__ pts, long long n, pomp_metric_desc m,
+                              const uint8_t* __restrict__ skip, const double* __restrict__ q, long long nq,
+                              int k, SplitGeom sg, double* __restrict__ part_d, int* __restrict__ part_i) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= nq * sg.nsplit) return;
+  long long qi = warp / sg.nsplit;
+  int sp = (int)(warp % sg.nsplit);
+  const int D = m.dim;
+  double qq[POMP_MAX_DIM], p[POMP_MAX_DIM];
+  load_q(q + qi * D, D, qq);
+  long long b = (long long)sp * sg.chunk, e = min(n, b + sg.chunk);
+  WarpTopK<KL, int> top;
+  top.init(k);
+  for (long long i0 = b; i0 < e; i0 += 32) {
+    long long i = i0 + lane;
+    double d = POMP_INF;
+    if (i < e && !(skip && skip[i])) {
+      for (int j = 0; j < D; j++) p[j] = __ldg(pts + i * D + j);
+      d = metric_eval(m, p, qq);
+    }
+    top.offer(d, (int)i);
+  }
+  top.store(part_d + warp * k, part_i + warp * k);
+}
+
+// merge `nlists` sorted-or-not candidate lists of length k per query into the k best
+template <int KL, typename InI>
+__global__ void merge_lists_kernel(const double* __restrict__ in_d, const InI* __restrict__ in_i, int nlists,
+                                   long long nq, int k, long long list_stride_q, long long list_stride_l,
+                                   int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                   int32_t* __restrict__ out_cnt) {
+  long long qi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  WarpTopK<KL, int64_t> top;
+  top.init(k);
+  for (int l = 0; l < nlists; l++) {
+    const double* ld = in_d + qi * list_stride_q + (long long)l * list_stride_l;
+    const InI* li = in_i + qi * list_stride_q + (long long)l * list_stride_l;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      int j = j0 + lane;
+      double d = POMP_INF;
+      int64_t id = 0;
+      if (j < k) {
+        id = (int64_t)li[j];
+        d = id >= 0 ? ld[j] : POMP_INF;
+      }
+      top.offer(d, id);
+    }
+  }
+  int cnt = top.store(out_dist + qi * k, out_idx + qi * k);
+  if (lane == 0 && out_cnt) out_cnt[qi] = cnt;
+}
+
+// radius: per (query, split) hit counts, then fill in index order
+template <bool FILL>
+__global__ void bf_radius_kernel(const double* __restrict__ pts, long long n, pomp_metric_desc m,
+                                 const uint8_t* __restrict__ skip, const double* __restrict__ q, long long nq,
+                                 double radius, int inclusive, SplitGeom sg, int* __restrict__ counts,
+                                 const int64_t* __restrict__ offsets, int64_t* __restrict__ out) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= nq * sg.nsplit) return;
+  long long qi = warp / sg.nsplit;
+  int sp = (int)(warp % sg.nsplit);
+  const int D = m.dim;
+  double qq[POMP_MAX_DIM], p[POMP_MAX_DIM];
+  load_q(q + qi * D, D, qq);
+  long long b = (long long)sp * sg.chunk, e = min(n, b + sg.chunk);
+  long long cnt = 0;
+  int64_t base = FILL ? offsets[warp] : 0;
+  for (long long i0 = b; i0 < e; i0 += 32) {
+    long long i = i0 + lane;
+    bool hit = false;
+    if (i < e && !(skip && skip[i])) {
+      for (int j = 0; j < D; j++) p[j] = __ldg(pts + i * D + j);
+      double d = metric_eval(m, p, qq);
+      hit = inclusive ? (d <= radius) : (d < radius);
+    }
+    unsigned mask = __ballot_sync(FULL_MASK, hit);
+    if (FILL && hit) out[base + cnt + __popc(mask & ((1u << lane) - 1))] = i;
+    cnt += __popc(mask);
+  }
+  if (!FILL && lane == 0) counts[warp] = (int)cnt;
+}
+
+// ============================================================================ grid build kernels
+__global__ void bbox_kernel(const double* __restrict__ pts, long long n, int D, double* __restrict__ part) {
+  double mn[POMP_MAX_DIM], mx[POMP_MAX_DIM];
+  for (int j = 0; j < D; j++) {
+    mn[j] = POMP_INF;
+    mx[j] = -POMP_INF;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    for (int j = 0; j < D; j++) {
+      double v = pts[i * D + j];
+      mn[j] = fmin(mn[j], v);
+      mx[j] = fmax(mx[j], v);
+    }
+  __shared__ double smn[32][POMP_MAX_DIM], smx[32][POMP_MAX_DIM];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = 0; j < D; j++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[j] = fmin(mn[j], __shfl_xor_sync(FULL_MASK, mn[j], o));
+      mx[j] = fmax(mx[j], __shfl_xor_sync(FULL_MASK, mx[j], o));
+    }
+    if (lane == 0) {
+      smn[w][j] = mn[j];
+      smx[w][j] = mx[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    int j = threadIdx.x;
+    double a = POMP_INF, b = -POMP_INF;
+    for (int x = 0; x < nw; x++) {
+      a = fmin(a, smn[x][j]);
+      b = fmax(b, smx[x][j]);
+    }
+    part[((long long)blockIdx.x * 2 + 0) * POMP_MAX_DIM + j] = a;
+    part[((long long)blockIdx.x * 2 + 1) * POMP_MAX_DIM + j] = b;
+  }
+}
+
+__device__ __forceinline__ long long grid_cell_id(const GridDev& g, const double* p) {
+  long long id = 0;
+  for (int a = 0; a < g.G; a++) id += (long long)grid_cell(g, a, p[g.gdim[a]]) * g.stride[a];
+  return id;
+}
+
+__global__ void cell_count_kernel(GridDev g, const double* __restrict__ pts, long long n, int D,
+                                  int* __restrict__ counts, int* __restrict__ slot) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[POMP_MAX_DIM];
+  for (int j = 0; j < D; j++) p[j] = pts[i * D + j];
+  long long c = grid_cell_id(g, p);
+  slot[i] = atomicAdd(counts + c, 1);
+}
+
+__global__ void cell_scatter_kernel(GridDev g, const double* __restrict__ pts, long long n, int D,
+                                    const int* __restrict__ cell_start, const int* __restrict__ slot,
+                                    double* __restrict__ spts, int* __restrict__ sidx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[POMP_MAX_DIM];
+  for (int j = 0; j < D; j++) p[j] = pts[i * D + j];
+  long long c = grid_cell_id(g, p);
+  long long pos = (long long)cell_start[c] + slot[i];
+  for (int j = 0; j < D; j++) spts[pos * D + j] = p[j];
+  sidx[pos] = (int)i;
+}
+
+// query ordering by home cell (counting sort with the index's own cells)
+__global__ void query_cell_kernel(GridDev g, const double* __restrict__ q, long long nq, int D,
+                                  int* __restrict__ counts, int* __restrict__ qcell, int* __restrict__ slot) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  double p[POMP_MAX_DIM];
+  for (int j = 0; j < D; j++) p[j] = q[i * D + j];
+  long long c = grid_cell_id(g, p);
+  qcell[i] = (int)c;
+  slot[i] = atomicAdd(counts + c, 1);
+}
+
+__global__ void query_perm_kernel(const int* __restrict__ qcell, const int* __restrict__ slot,
+                                  const int* __restrict__ start, long long nq, int* __restrict__ perm) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  perm[start[qcell[i]] + slot[i]] = (int)i;
+}
+
+// ============================================================================ grid query kernels
+template <int K>
+struct KnnColl {
+  ThreadTopK<K>& top;
+  const int* __restrict__ sidx;
+  __device__ __forceinline__ double threshold() const { return top.threshold(); }
+  __device__ __forceinline__ void offer(double d, long long pos) {
+    if (top.maybe(d)) top.insert(d, __ldg(sidx + pos));
+  }
+};
+
+// D = 0: runtime dimension (generic metrics)
+template <int D, int K, bool EUCLID>
+__global__ void __launch_bounds__(128)
+grid_knn_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts, long long n,
+                const uint8_t* __restrict__ skip, const double* __restrict__ q, long long nq,
+                const int* __restrict__ qperm, int k, int64_t* __restrict__ out_idx,
+                double* __restrict__ out_dist, int32_t* __restrict__ out_cnt) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  long long qi = qperm ? (long long)qperm[t] : t;
+  constexpr int DA = D ? D : POMP_MAX_DIM;
+  const int dim = D ? D : m.dim;
+  double qq[DA];
+#pragma unroll
+  for (int j = 0; j < DA; j++) qq[j] = j < dim ? q[qi * dim + j] : 0.0;
+  ThreadTopK<K> top;
+  top.init(k);
+  KnnColl<K> coll{top, g.sidx};
+  // phase A: any k real points bound the k-th distance from above; take them next to the query's
+  // home cell in the sorted order (spatially close), growing the window while masked points hide it
+  long long home = 0;
+  for (int a = 0; a < g.G; a++) home += (long long)grid_cell(g, a, qq[g.gdim[a]]) * g.stride[a];
+  int hs = __ldg(g.cell_start + home), he = __ldg(g.cell_start + home + 1);
+  int center = (hs + he) >> 1;
+  int w0 = max(0, center - k), w1 = min(g.n_indexed, center + k);
+  {
+    int a0 = w0, a1 = w1;
+    while (true) {
+      for (int pos = a0; pos < a1; pos++) {
+        if (skip && skip[__ldg(g.sidx + pos)]) continue;
+        double p[DA];
+        if (D) load_point<DA>(g.spts, pos, p);
+        else
+          for (int j = 0; j < dim; j++) p[j] = __ldg(g.spts + (long long)pos * dim + j);
+        coll.offer(D ? point_dist<DA, EUCLID>(m, p, qq) : metric_eval(m, p, qq), pos);
+      }
+      if (top.full() || (w0 == 0 && w1 == g.n_indexed)) break;
+      // grow to the left, then to the right
+      int len = w1 - w0;
+      if (w0 > 0) {
+        a1 = w0;
+        w0 = max(0, w0 - len);
+        a0 = w0;
+      } else {
+        a0 = w1;
+        w1 = min(g.n_indexed, w1 + len);
+        a1 = w1;
+      }
+    }
+  }
+  grid_visit<D, EUCLID>(g, m, skip, qq, coll, w0, w1);
+  // points appended after the last index build
+  for (long long i = g.n_indexed; i < n; i++) {
+    if (skip && skip[i]) continue;
+    double p[DA];
+    for (int j = 0; j < dim; j++) p[j] = __ldg(pts + i * dim + j);
+    double d = (D && EUCLID) ? euclid_fixed<DA>(p, qq) : metric_eval(m, p, qq);
+    if (top.maybe(d)) top.insert(d, (int)i);
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++)
+    if (j < k) {
+      bool fin = top.d[j] < POMP_INF;
+      out_idx[qi * k + j] = fin ? (int64_t)top.i[j] : -1;
+      out_dist[qi * k + j] = top.d[j];
+      cnt += fin;
+    }
+  if (out_cnt) out_cnt[qi] = cnt;
+}
+
+template <bool FILL>
+struct RadiusColl {
+  double radius;
+  int inclusive;
+  long long cnt;
+  const int* __restrict__ sidx;
+  int64_t* out;
+  __device__ __forceinline__ double threshold() const { return radius; }
+  __device__ __forceinline__ void offer_idx(double d, long long idx) {
+    bool hit = inclusive ? (d <= radius) : (d < radius);
+    if (hit) {
+      if (FILL) out[cnt] = idx;
+      cnt++;
+    }
+  }
+  __device__ __forceinline__ void offer(double d, long long pos) {
+    bool hit = inclusive ? (d <= radius) : (d < radius);
+    if (hit) {
+      if (FILL) out[cnt] = __ldg(sidx + pos);
+      cnt++;
+    }
+  }
+};
+
+__device__ __forceinline__ void heapsort_i64(int64_t* a, long long n) {
+  if (n < 2) return;
+  for (long long start = n / 2 - 1; start >= 0; start--) {
+    long long root = start;
+    while (true) {
+      long long child = 2 * root + 1;
+      if (child >= n) break;
+      if (child + 1 < n && a[child] < a[child + 1]) child++;
+      if (a[root] >= a[child]) break;
+      int64_t t = a[root];
+      a[root] = a[child];
+      a[child] = t;
+      root = child;
+    }
+  }
+  for (long long end = n - 1; end > 0; end--) {
+    int64_t t = a[0];
+    a[0] = a[end];
+    a[end] = t;
+    long long root = 0;
+    while (true) {
+      long long child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && a[child] < a[child + 1]) child++;
+      if (a[root] >= a[child]) break;
+      int64_t t2 = a[root];
+      a[root] = a[child];
+      a[child] = t2;
+      root = child;
+    }
+  }
+}
+
+template <int D, bool EUCLID, bool FILL>
+__global__ void __launch_bounds__(128)
+grid_radius_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts, long long n,
+                   const uint8_t* __restrict__ skip, const double* __restrict__ q, long long nq, double radius,
+                   int inclusive, int* __restrict__ counts, const int64_t* __restrict__ offsets,
+                   int64_t* __restrict__ out) {
+  long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  constexpr int DA = D ? D : POMP_MAX_DIM;
+  const int dim = D ? D : m.dim;
+  double qq[DA];
+#pragma unroll
+  for (int j = 0; j < DA; j++) qq[j] = j < dim ? q[qi * dim + j] : 0.0;
+  RadiusColl<FILL> coll{radius, inclusive, 0, g.sidx, FILL ? out + offsets[qi] : nullptr};
+  grid_visit<D, EUCLID>(g, m, skip, qq, coll, 0, 0);
+  for (long long i = g.n_indexed; i < n; i++) {
+    if (skip && skip[i]) continue;
+    double p[DA];
+    for (int j = 0; j < dim; j++) p[j] = __ldg(pts + i * dim + j);
+    coll.offer_idx((D && EUCLID) ? euclid_fixed<DA>(p, qq) : metric_eval(m, p, qq), i);
+  }
+  if (FILL) heapsort_i64(out + offsets[qi], coll.cnt);
+  else counts[qi] = (int)coll.cnt;
+}
+
+// ============================================================================ host: grid build
+static void axis_scales(const pomp_metric_desc& m, double* s /*[base_dim]*/) {
+  int d = base_dim(m);
+  for (int i = 0; i < d; i++) s[i] = 0.0;
+  if (m.has_cost && m.cost_weight_set && !(m.cost_weight >= 0.0)) return;  // bound needs cost term >= 0
+  switch (m.kind) {
+    case POMP_METRIC_EUCLIDEAN:
+    case POMP_METRIC_L1:
+    case POMP_METRIC_LINF:
+      for (int i = 0; i < d; i++) s[i] = 1.0;
+      break;
+    case POMP_METRIC_SCALED_EUCLIDEAN:
+      if (m.scale > 0.0)
+        for (int i = 0; i < d; i++) s[i] = m.scale;
+      break;
+    case POMP_METRIC_WEIGHTED_EUCLIDEAN: {
+      bool ok = true;
+      for (int i = 0; i < d; i++) ok = ok && (m.dim_weight[i] >= 0.0);
+      if (ok)
+        for (int i = 0; i < d; i++) s[i] = m.dim_weight[i] > 0.0 ? sqrt(m.dim_weight[i]) : 0.0;
+      break;
+    }
+    case POMP_METRIC_GEODESIC_PRODUCT: {
+      bool ok = true;
+      for (int c = 0; c < m.n_comp; c++) ok = ok && (m.comp_weight[c] >= 0.0);
+      if (!ok) break;
+      int i = 0;
+      for (int c = 0; c < m.n_comp; c++)
+        for (int j = 0; j < m.comp_dim[c]; j++, i++)
+          s[i] = (m.comp_kind[c] == POMP_COMP_CARTESIAN && m.comp_weight[c] > 0.0) ? sqrt(m.comp_weight[c]) : 0.0;
+      break;
+    }
+  }
+}
+
+static int build_grid(pomp_nn* h, cudaStream_t st) {
+  POMP_TRY(nn_flush(h, st));
+  h->grid_valid = false;
+  const int D = h->D;
+  const int64_t n = h->n_dev;
+  POMP_REQUIRE(n > 0, "cannot index an empty point set");
+  POMP_REQUIRE(n < (int64_t)0x7fffffff, "more than 2^31-1 points per shard are not supported");
+  double s[POMP_MAX_DIM];
+  axis_scales(h->metric, s);
+  // bounding box
+  int nb = std::min<int64_t>((n + 255) / 256, (int64_t)sm_count(h->device) * 8);
+  POMP_TRY(h->part_d.reserve((size_t)nb * 2 * POMP_MAX_DIM));
+  LAUNCH(bbox_kernel, nb, 256, 0, st, h->d_pts, (long long)n, D, h->part_d.p);
+  CHECK_LAUNCH();
+  std::vector<double> part((size_t)nb * 2 * POMP_MAX_DIM);
+  CUDA_TRY(cudaMemcpyAsync(part.data(), h->part_d.p, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  double lo[POMP_MAX_DIM], hi[POMP_MAX_DIM];
+  for (int j = 0; j < D; j++) {
+    lo[j] = INFINITY;
+    hi[j] = -INFINITY;
+    for (int b = 0; b < nb; b++) {
+      lo[j] = fmin(lo[j], part[((size_t)b * 2 + 0) * POMP_MAX_DIM + j]);
+      hi[j] = fmax(hi[j], part[((size_t)b * 2 + 1) * POMP_MAX_DIM + j]);
+    }
+  }
+  GridDev g;
+  memset(&g, 0, sizeof(g));
+  int G = 0;
+  double wext[POMP_MAX_DIM];
+  for (int j = 0; j < base_dim(h->metric); j++) {
+    double ext = hi[j] - lo[j];
+    if (s[j] > 0.0 && isfinite(lo[j]) && isfinite(hi[j]) && ext > 0.0 && isfinite(ext)) {
+      g.gdim[G] = j;
+      g.lo[G] = lo[j];
+      g.hi[G] = hi[j];
+      wext[G] = ext * s[j];
+      g.rscale[G] = (1.0 + 1e-9) / s[j];
+      g.slack[G] = 1e-9 * fmax(fmax(fabs(lo[j]), fabs(hi[j])), ext) + 1e-300;
+      G++;
+    }
+  }
+  if (G == 0) {
+    h->grid_unusable = true;
+    set_error("metric/point set gives no usable grid axis");
+    return POMP_ERR_INVALID;
+  }
+  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G <= 2 ? 4.0 : (G == 3 ? 8.0 : 16.0));
+  double target = fmax(1.0, (double)n / ppc);
+  target = fmin(target, 268435456.0);
+  // cubic cells in metric space: ncell_a proportional to the weighted extent
+  double logvol = 0;
+  for (int a = 0; a < G; a++) logvol += log(wext[a]);
+  double cell = exp((logvol - log(target)) / G);
+  long long total = 1;
+  for (int a = 0; a < G; a++) {
+    long long nc = (long long)floor(wext[a] / cell + 0.5);
+    nc = std::max<long long>(1, std::min<long long>(nc, 1 << 20));
+    g.ncell[a] = (int)nc;
+    total *= nc;
+  }
+  while (total > 536870912LL) {  // safety cap: halve the finest axis
+    int am = 0;
+    for (int a = 1; a < G; a++)
+      if (g.ncell[a] > g.ncell[am]) am = a;
+    total /= g.ncell[am];
+    g.ncell[am] = std::max(1, g.ncell[am] / 2);
+    total *= g.ncell[am];
+  }
+  long long stride = 1;
+  for (int a = 0; a < G; a++) {
+    double ext = g.hi[a] - g.lo[a];
+    g.h[a] = ext / (double)g.ncell[a];
+    g.inv_h[a] = (double)g.ncell[a] / ext;
+    g.stride[a] = stride;
+    stride *= g.ncell[a];
+  }
+  g.G = G;
+  g.n_cells = total;
+  g.n_indexed = (int)n;
+  // counting sort of the points by cell id
+  POMP_TRY(h->cell_start.reserve((size_t)total + 1));
+  POMP_TRY(h->tmp_i32.reserve((size_t)n + (size_t)total));
+  POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(total)));
+  POMP_TRY(h->spts.reserve((size_t)n * D));
+  POMP_TRY(h->sidx.reserve((size_t)n));
+  int* slot = h->tmp_i32.p;
+  int* counts = h->tmp_i32.p + n;
+  CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)total, st));
+  int blocks = (int)((n + 255) / 256);
+  LAUNCH(cell_count_kernel, blocks, 256, 0, st, g, h->d_pts, (long long)n, D, counts, slot);
+  POMP_TRY(exclusive_scan<int>(counts, total, h->cell_start.p, h->scan_tmp.p, st));
+  LAUNCH(cell_scatter_kernel, blocks, 256, 0, st, g, h->d_pts, (long long)n, D, h->cell_start.p, slot, h->spts.p,
+         h->sidx.p);
+  CHECK_LAUNCH();
+  g.cell_start = h->cell_start.p;
+  g.spts = h->spts.p;
+  g.sidx = h->sidx.p;
+  h->grid = g;
+  h->grid_valid = true;
+  h->grid_unusable = false;
+  return POMP_OK;
+}
+
+// decide the regime for a batch of nq queries; builds the index when it pays
+static int want_grid(pomp_nn* h, int64_t nq, bool* use, cudaStream_t st) {
+  *use = false;
+  int64_t n = h->size();
+  if (h->grid_unusable || n < (int64_t)h->grid_min_points || nq < (int64_t)h->grid_min_queries) return POMP_OK;
+  POMP_TRY(nn_flush(h, st));
+  if (!h->grid_valid || (h->n_dev - h->grid.n_indexed) > (int64_t)h->max_tail) {
+    int rc = build_grid(h, st);
+    if (rc == POMP_ERR_INVALID && h->grid_unusable) return POMP_OK;  // fall back to brute force kernels
+    POMP_TRY(rc);
+  }
+  *use = true;
+  return POMP_OK;
+}
+
+static SplitGeom split_geom(pomp_nn* h, int64_t nq, int64_t n) {
+  SplitGeom sg;
+  long long want_warps = (long long)sm_count(h->device) * 32;
+  long long ns = nq >= want_warps ? 1 : (want_warps + nq - 1) / std::max<int64_t>(nq, 1);
+  long long max_ns = std::max<long long>(1, (n + 255) / 256);  // at least 256 points per warp
+  ns = std::max<long long>(1, std::min(ns, max_ns));
+  sg.nsplit = (int)ns;
+  sg.chunk = std::max<long long>(1, (n + ns - 1) / ns);
+  return sg;
+}
+
+static bool is_plain_euclid(const pomp_metric_desc& m) { return m.kind == POMP_METRIC_EUCLIDEAN && !m.has_cost; }
+
+// ---- k-NN dispatch ---------------------------------------------------------------------------
+template <int D, bool EUCLID>
+static int launch_grid_knn(pomp_nn* h, const double* q, int64_t nq, const int* qperm, int k, int64_t* idx,
+                           double* dist, int32_t* cnt, cudaStream_t st) {
+  int blocks = (int)((nq + 127) / 128);
+  const uint8_t* skip = h->skip_ptr();
+#define GK(KK)                                                                                              \
+  LAUNCH((grid_knn_kernel<D, KK, EUCLID>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts, (long long)h->n_dev, \
+         skip, q, (long long)nq, qperm, k, idx, dist, cnt)
+  if (k == 1) GK(1);
+  else if (k <= 4) GK(4);
+  else if (k <= 8) GK(8);
+  else if (k <= 16) GK(16);
+  else if (k <= 32) GK(32);
+  else if (k <= 64) GK(64);
+  else GK(128);
+#undef GK
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
+                    cudaStream_t st) {
+  const int* qperm = nullptr;
+  if (h->sort_queries != 0 && nq >= 32768 && h->grid.n_cells <= 0x7fffffff) {
+    long long nc = h->grid.n_cells;
+    POMP_TRY(h->counts.reserve((size_t)nc + 1 + (size_t)nc + 1));
+    POMP_TRY(h->qcell.reserve((size_t)nq * 2));
+    POMP_TRY(h->qperm.reserve((size_t)nq));
+    POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(nc)));
+    int* counts = h->counts.p;
+    int* start = h->counts.p + nc + 1;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nc, st));
+    int blocks = (int)((nq + 255) / 256);
+    LAUNCH(query_cell_kernel, blocks, 256, 0, st, h->grid, q, (long long)nq, h->D, counts, h->qcell.p,
+           h->qcell.p + nq);
+    POMP_TRY(exclusive_scan<int>(counts, nc, start, h->scan_tmp.p, st));
+    LAUNCH(query_perm_kernel, blocks, 256, 0, st, h->qcell.p, h->qcell.p + nq, start, (long long)nq, h->qperm.p);
+    CHECK_LAUNCH();
+    qperm = h->qperm.p;
+  }
+  if (is_plain_euclid(h->metric)) {
+    switch (h->D) {
+      case 2: return launch_grid_knn<2, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 3: return launch_grid_knn<3, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 4: return launch_grid_knn<4, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 6: return launch_grid_knn<6, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      default: break;
+    }
+  }
+  return launch_grid_knn<0, false>(h, q, nq, qperm, k, idx, dist, cnt, st);
+}
+
+static int bf_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
+                  cudaStream_t st) {
+  const int64_t n = h->n_dev;
+  SplitGeom sg = split_geom(h, nq, n);
+  long long warps = (long long)nq * sg.nsplit;
+  int blocks = (int)((warps * 32 + 255) / 256);
+  const uint8_t* skip = h->skip_ptr();
+  if (k == 1) {
+    POMP_TRY(h->part_d.reserve((size_t)warps));
+    POMP_TRY(h->part_i.reserve((size_t)warps));
+    LAUNCH(bf_nearest_kernel, blocks, 256, 0, st, h->d_pts, (long long)n, h->metric, skip, q, (long long)nq, sg,
+           h->part_d.p, h->part_i.p);
+    LAUNCH(bf_nearest_reduce_kernel, (int)((nq + 255) / 256), 256, 0, st, h->part_d.p, h->part_i.p, (long long)nq,
+           sg.nsplit, idx, dist);
+    CHECK_LAUNCH();
+    if (cnt) {
+      // count = (idx >= 0); done by the merge kernel path below for k>1, here by a tiny memset-free trick:
+      // reuse merge kernel with one list of length 1
+      LAUNCH((merge_lists_kernel<1, int64_t>), (int)((nq * 32 + 255) / 256), 256, 0, st, dist, idx, 1, (long long)nq, 1,
+             1LL, 1LL, idx, dist, cnt);
+      CHECK_LAUNCH();
+    }
+    return POMP_OK;
+  }
+  POMP_TRY(h->part_d.reserve((size_t)warps * k));
+  POMP_TRY(h->part_i.reserve((size_t)warps * k));
+  int mblocks = (int)((nq * 32 + 255) / 256);
+#define BK(KL)                                                                                                     \
+  do {                                                                                                             \
+    LAUNCH((bf_knn_kernel<KL>), blocks, 256, 0, st, h->d_pts, (long long)n, h->metric, skip, q, (long long)nq, k, sg, \
+           h->part_d.p, h->part_i.p);                                                                              \
+    LAUNCH((merge_lists_kernel<KL, int>), mblocks, 256, 0, st, h->part_d.p, h->part_i.p, sg.nsplit, (long long)nq, k, \
+           (long long)sg.nsplit * k, (long long)k, idx, dist, cnt);                                                \
+  } while (0)
+  if (k <= 32) BK(1);
+  else if (k <= 64) BK(2);
+  else BK(4);
+#undef BK
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+static int knn_device(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
+                      cudaStream_t st) {
+  POMP_REQUIRE(k >= 1 && k <= 128, "k=%d outside 1..128", k);
+  if (nq == 0) return POMP_OK;
+  POMP_TRY(nn_flush(h, st));
+  bool use_grid = false;
+  POMP_TRY(want_grid(h, nq, &use_grid, st));
+  if (use_grid) return grid_knn(h, q, nq, k, idx, dist, cnt, st);
+  return bf_knn(h, q, nq, k, idx, dist, cnt, st);
+}
+
+// ---- radius dispatch -------------------------------------------------------------------------
+template <int D, bool EUCLID>
+static int launch_grid_radius(pomp_nn* h, bool fill, const double* q, int64_t nq, double radius, int inclusive,
+                              int* counts, const int64_t* offsets, int64_t* out, cudaStream_t st) {
+  int blocks = (int)((nq + 127) / 128);
+  const uint8_t* skip = h->skip_ptr();
+  if (fill)
+    LAUNCH((grid_radius_kernel<D, EUCLID, true>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts,
+           (long long)h->n_dev, skip, q, (long long)nq, radius, inclusive, counts, offsets, out);
+  else
+    LAUNCH((grid_radius_kernel<D, EUCLID, false>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts,
+           (long long)h->n_dev, skip, q, (long long)nq, radius, inclusive, counts, offsets, out);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+static int grid_radius(pomp_nn* h, bool fill, const double* q, int64_t nq, double radius, int inclusive,
+                       int* counts, const int64_t* offsets, int64_t* out, cudaStream_t st) {
+  if (is_plain_euclid(h->metric)) {
+    switch (h->D) {
+      case 2: return launch_grid_radius<2, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      case 3: return launch_grid_radius<3, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      case 4: return launch_grid_radius<4, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      case 6: return launch_grid_radius<6, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      default: break;
+    }
+  }
+  return launch_grid_radius<0, false>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+}
+
+// offsets: device int64 [nq+1]; returns total through *needed_h (synchronises)
+static int radius_device(pomp_nn* h, const double* q, int64_t nq, double radius, int inclusive, int64_t* offsets,
+                         int64_t* idx, int64_t idx_capacity, int64_t* needed_h, cudaStream_t st) {
+  if (needed_h) *needed_h = 0;
+  if (nq == 0) {
+    CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(int64_t), st));
+    return POMP_OK;
+  }
+  POMP_TRY(nn_flush(h, st));
+  bool use_grid = false;
+  POMP_TRY(want_grid(h, nq, &use_grid, st));
+  const int64_t n = h->n_dev;
+  const uint8_t* skip = h->skip_ptr();
+  int64_t total = 0;
+  if (use_grid) {
+    POMP_TRY(h->counts.reserve((size_t)nq + 1));
+    POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(nq)));
+    POMP_TRY(grid_radius(h, false, q, nq, radius, inclusive, h->counts.p, nullptr, nullptr, st));
+    POMP_TRY(exclusive_scan<int64_t>(h->counts.p, nq, offsets, h->scan_tmp.p, st));
+    CUDA_TRY(cudaMemcpyAsync(&total, offsets + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (needed_h) *needed_h = total;
+    if (total > idx_capacity) {
+      set_error("radius query produced %lld hits, capacity %lld", (long long)total, (long long)idx_capacity);
+      return POMP_ERR_CAPACITY;
+    }
+    if (total > 0) POMP_TRY(grid_radius(h, true, q, nq, radius, inclusive, nullptr, offsets, idx, st));
+    return POMP_OK;
+  }
+  SplitGeom sg = split_geom(h, nq, n);
+  long long warps = (long long)nq * sg.nsplit;
+  int blocks = (int)((warps * 32 + 255) / 256);
+  POMP_TRY(h->counts.reserve((size_t)warps + 1));
+  POMP_TRY(h->out_off.reserve((size_t)warps + 1));
+  POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(warps)));
+  LAUNCH((bf_radius_kernel<false>), blocks, 256, 0, st, h->d_pts, (long long)n, h->metric, skip, q, (long long)nq,
+         radius, inclusive, sg, h->counts.p, nullptr, nullptr);
+  POMP_TRY(exclusive_scan<int64_t>(h->counts.p, warps, h->out_off.p, h->scan_tmp.p, st));
+  // per-query offsets are every nsplit-th entry of the per-warp offsets
+  CUDA_TRY(cudaMemcpy2DAsync(offsets, sizeof(int64_t), h->out_off.p, sizeof(int64_t) * sg.nsplit, sizeof(int64_t),
+                             (size_t)nq, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(offsets + nq, h->out_off.p + warps, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(&total, h->out_off.p + warps, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (needed_h) *needed_h = total;
+  if (total > idx_capacity) {
+    set_error("radius query produced %lld hits, capacity %lld", (long long)total, (long long)idx_capacity);
+    return POMP_ERR_CAPACITY;
+  }
+  if (total > 0) {
+    LAUNCH((bf_radius_kernel<true>), blocks, 256, 0, st, h->d_pts, (long long)n, h->metric, skip, q, (long long)nq,
+           radius, inclusive, sg, nullptr, h->out_off.p, idx);
+    CHECK_LAUNCH();
+  }
+  return POMP_OK;
+}
+
+// ============================================================================ C ABI
+POMP_API int pomp_nn_create(const pomp_metric_desc* metric, int64_t capacity_hint, int device, pomp_nn** out) {
+  POMP_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  POMP_TRY(validate_metric(metric));
+  DeviceGuard g(device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  pomp_nn* h = new pomp_nn();
+  h->device = device;
+  h->metric = *metric;
+  h->D = metric->dim;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaHostAlloc(&h->mailbox_h, sizeof(Mailbox), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->mailbox_d, h->mailbox_h, 0);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    set_error("pomp_nn_create: %s", cudaGetErrorString(e));
+    delete h;
+    return POMP_ERR_CUDA;
+  }
+  int rc = nn_grow(h, std::max<int64_t>(capacity_hint, 1024), h->stream);
+  if (rc != POMP_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_destroy(pomp_nn* h) {
+  if (!h) return POMP_OK;
+  DeviceGuard g(h->device);
+  if (h->d_pts) cudaFree(h->d_pts);
+  if (h->d_skip) cudaFree(h->d_skip);
+  if (h->mailbox_h) cudaFreeHost(h->mailbox_h);
+  if (h->ticket) cudaFree(h->ticket);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_reset(pomp_nn* h) {
+  POMP_REQUIRE(h, "handle is NULL");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (h->any_dead || h->has_reject) CUDA_TRY(cudaMemsetAsync(h->d_skip, 0, (size_t)h->n_dev, h->stream));
+  h->n_dev = 0;
+  h->pending.clear();
+  h->h_dead.clear();
+  h->h_reject.clear();
+  h->any_dead = h->has_reject = false;
+  h->grid_valid = false;
+  h->grid_unusable = false;
+  return POMP_OK;
+}
+
+POMP_API int64_t pomp_nn_size(const pomp_nn* h) { return h ? h->size() : 0; }
+
+POMP_API int pomp_nn_add_h(pomp_nn* h, const double* pts_h, int64_t n, int64_t* first_index_out_h) {
+  POMP_REQUIRE(h && (pts_h || n == 0) && n >= 0, "bad arguments to pomp_nn_add_h");
+  if (first_index_out_h) *first_index_out_h = h->size();
+  h->pending.insert(h->pending.end(), pts_h, pts_h + n * h->D);
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_add(pomp_nn* h, const double* pts, int64_t n, int64_t* first_index_out_h, void* stream) {
+  POMP_REQUIRE(h && (pts || n == 0) && n >= 0, "bad arguments to pomp_nn_add");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  POMP_TRY(nn_flush(h, st));
+  if (first_index_out_h) *first_index_out_h = h->n_dev;
+  POMP_TRY(nn_grow(h, h->n_dev + n, st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts + h->n_dev * h->D, pts, sizeof(double) * (size_t)n * h->D,
+                           cudaMemcpyDeviceToDevice, st));
+  h->n_dev += n;
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_set(pomp_nn* h, const double* pts, int64_t n, void* stream) {
+  POMP_TRY(pomp_nn_reset(h));
+  POMP_TRY(pomp_nn_add(h, pts, n, nullptr, stream));
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_set_h(pomp_nn* h, const double* pts_h, int64_t n) {
+  POMP_TRY(pomp_nn_reset(h));
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  POMP_REQUIRE((pts_h || n == 0) && n >= 0, "bad arguments to pomp_nn_set_h");
+  POMP_TRY(nn_grow(h, n, h->stream));
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_pts, pts_h, sizeof(double) * (size_t)n * h->D, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  h->n_dev = n;
+  return POMP_OK;
+}
+
+static int upload_skip(pomp_nn* h) {
+  int64_t n = h->size();
+  POMP_TRY(nn_flush(h, h->stream));
+  std::vector<uint8_t> comb((size_t)n, 0);
+  for (int64_t i = 0; i < n; i++) {
+    uint8_t v = 0;
+    if ((size_t)i < h->h_dead.size()) v |= h->h_dead[i];
+    if (h->has_reject && (size_t)i < h->h_reject.size()) v |= h->h_reject[i];
+    comb[i] = v ? 1 : 0;
+  }
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_skip, comb.data(), (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_remove(pomp_nn* h, int64_t index) {
+  POMP_REQUIRE(h, "handle is NULL");
+  POMP_REQUIRE(index >= 0 && index < h->size(), "remove index %lld out of range", (long long)index);
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (h->h_dead.size() < (size_t)h->size()) h->h_dead.resize((size_t)h->size(), 0);
+  h->h_dead[index] = 1;
+  h->any_dead = true;
+  POMP_TRY(nn_flush(h, h->stream));
+  uint8_t one = 1;
+  CUDA_TRY(cudaMemcpyAsync(h->d_skip + index, &one, 1, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_set_mask_h(pomp_nn* h, const uint8_t* reject_mask_h, int64_t n) {
+  POMP_REQUIRE(h, "handle is NULL");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (!reject_mask_h) {
+    if (!h->has_reject) return POMP_OK;
+    h->has_reject = false;
+    h->h_reject.clear();
+    return upload_skip(h);
+  }
+  POMP_REQUIRE(n == h->size(), "mask length %lld != point count %lld", (long long)n, (long long)h->size());
+  h->h_reject.assign(reject_mask_h, reject_mask_h + n);
+  h->has_reject = true;
+  return upload_skip(h);
+}
+
+POMP_API int pomp_nn_update_metric(pomp_nn* h, const pomp_metric_desc* metric) {
+  POMP_REQUIRE(h, "handle is NULL");
+  POMP_TRY(validate_metric(metric));
+  POMP_REQUIRE(metric->dim == h->D, "metric dim %d != point dim %d", metric->dim, h->D);
+  // the grid layout depends on the metric's per-axis scales; cost bounds/weights do not touch it
+  double s0[POMP_MAX_DIM], s1[POMP_MAX_DIM];
+  axis_scales(h->metric, s0);
+  axis_scales(*metric, s1);
+  bool same = (metric->kind == h->metric.kind) && (metric->has_cost == h->metric.has_cost);
+  for (int i = 0; i < base_dim(*metric) && same; i++) same = (s0[i] == s1[i]);
+  h->metric = *metric;
+  if (!same) {
+    h->grid_valid = false;
+    h->grid_unusable = false;
+  }
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
+  POMP_REQUIRE(h && name, "bad arguments to pomp_nn_set_param");
+  std::string s(name);
+  if (s == "grid_min_points") h->grid_min_points = value;
+  else if (s == "points_per_cell") {
+    h->points_per_cell = value;
+    h->grid_valid = false;
+  } else if (s == "sort_queries") h->sort_queries = value;
+  else if (s == "grid_min_queries") h->grid_min_queries = value;
+  else if (s == "max_tail") h->max_tail = value;
+  else {
+    set_error("unknown parameter '%s'", name);
+    return POMP_ERR_INVALID;
+  }
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_build_index(pomp_nn* h, void* stream) {
+  POMP_REQUIRE(h, "handle is NULL");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  return build_grid(h, (cudaStream_t)stream);
+}
+
+POMP_API int pomp_nn_knearest(pomp_nn* h, const double* q, int64_t nq, int32_t k, int64_t* idx, double* dist,
+                              int32_t* count, void* stream) {
+  POMP_REQUIRE(h && (nq == 0 || (q && idx && dist)) && nq >= 0, "bad arguments to pomp_nn_knearest");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  return knn_device(h, q, nq, k, idx, dist, count, (cudaStream_t)stream);
+}
+
+POMP_API int pomp_nn_nearest(pomp_nn* h, const double* q, int64_t nq, int64_t* idx, double* dist, void* stream) {
+  return pomp_nn_knearest(h, q, nq, 1, idx, dist, nullptr, stream);
+}
+
+POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32_t k, int64_t* idx_h,
+                                double* dist_h, int32_t* count_h) {
+  POMP_REQUIRE(h && (nq == 0 || (q_h && idx_h && dist_h)) && nq >= 0, "bad arguments to pomp_nn_knearest_h");
+  POMP_REQUIRE(k >= 1 && k <= 128, "k=%d outside 1..128", k);
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (nq == 0) return POMP_OK;
+  cudaStream_t st = h->stream;
+  POMP_TRY(h->q_dev.reserve((size_t)nq * h->D));
+  POMP_TRY(h->out_idx.reserve((size_t)nq * k));
+  POMP_TRY(h->out_dist.reserve((size_t)nq * k));
+  POMP_TRY(h->out_cnt.reserve((size_t)nq));
+  CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, q_h, sizeof(double) * (size_t)nq * h->D, cudaMemcpyHostToDevice, st));
+  POMP_TRY(knn_device(h, h->q_dev.p, nq, k, h->out_idx.p, h->out_dist.p, count_h ? h->out_cnt.p : nullptr, st));
+  CUDA_TRY(cudaMemcpyAsync(idx_h, h->out_idx.p, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(dist_h, h->out_dist.p, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  if (count_h) CUDA_TRY(cudaMemcpyAsync(count_h, h->out_cnt.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_nearest_h(pomp_nn* h, const double* q_h, int64_t nq, int64_t* idx_h, double* dist_h) {
+  POMP_REQUIRE(h && (nq == 0 || (q_h && idx_h && dist_h)) && nq >= 0, "bad arguments to pomp_nn_nearest_h");
+  if (nq != 1) return pomp_nn_knearest_h(h, q_h, nq, 1, idx_h, dist_h, nullptr);
+  // planner fast path: query travels in the kernel arguments, the answer lands in mapped host memory
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  cudaStream_t st = h->stream;
+  POMP_TRY(nn_flush(h, st));
+  const int64_t n = h->n_dev;
+  if (n == 0) {
+    *idx_h = -1;
+    *dist_h = INFINITY;
+    return POMP_OK;
+  }
+  QueryArg qa;
+  for (int j = 0; j < POMP_MAX_DIM; j++) qa.v[j] = j < h->D ? q_h[j] : 0.0;
+  int blocks = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)sm_count(h->device) * 2);
+  blocks = std::max(blocks, 1);
+  int threads = n <= 256 ? 64 : 256;
+  POMP_TRY(h->part_d.reserve((size_t)blocks));
+  POMP_TRY(h->part_i.reserve((size_t)blocks));
+  LAUNCH(bf_single_nearest_kernel, blocks, threads, 0, st, h->d_pts, (long long)n, h->metric, h->skip_ptr(), qa,
+         h->part_d.p, h->part_i.p, h->ticket, (Mailbox*)h->mailbox_d);
+  CHECK_LAUNCH();
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const Mailbox* mb = (const Mailbox*)h->mailbox_h;
+  *idx_h = mb->idx;
+  *dist_h = mb->dist;
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_neighbors(pomp_nn* h, const double* q, int64_t nq, double radius, int inclusive,
+                               int64_t* offsets, int64_t* idx, int64_t idx_capacity, int64_t* needed_h,
+                               void* stream) {
+  POMP_REQUIRE(h && offsets && (nq == 0 || q) && nq >= 0 && idx_capacity >= 0, "bad arguments to pomp_nn_neighbors");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  return radius_device(h, q, nq, radius, inclusive, offsets, idx, idx_capacity, needed_h, (cudaStream_t)stream);
+}
+
+POMP_API int pomp_nn_neighbors_h(pomp_nn* h, const double* q_h, int64_t nq, double radius, int inclusive,
+                                 int64_t* offsets_h, int64_t* idx_h, int64_t idx_capacity, int64_t* needed_h) {
+  POMP_REQUIRE(h && offsets_h && (nq == 0 || q_h) && nq >= 0 && idx_capacity >= 0,
+               "bad arguments to pomp_nn_neighbors_h");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  cudaStream_t st = h->stream;
+  if (nq == 0) {
+    offsets_h[0] = 0;
+    if (needed_h) *needed_h = 0;
+    return POMP_OK;
+  }
+  POMP_TRY(h->q_dev.reserve((size_t)nq * h->D));
+  POMP_TRY(h->out_idx.reserve((size_t)std::max<int64_t>(idx_capacity, 1)));
+  DevBuf<int64_t> off;
+  POMP_TRY(off.reserve((size_t)nq + 1));
+  CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, q_h, sizeof(double) * (size_t)nq * h->D, cudaMemcpyHostToDevice, st));
+  int64_t needed = 0;
+  int rc = radius_device(h, h->q_dev.p, nq, radius, inclusive, off.p, h->out_idx.p, idx_capacity, &needed, st);
+  if (needed_h) *needed_h = needed;
+  if (rc != POMP_OK && rc != POMP_ERR_CAPACITY) return rc;
+  CUDA_TRY(cudaMemcpyAsync(offsets_h, off.p, sizeof(int64_t) * (size_t)(nq + 1), cudaMemcpyDeviceToHost, st));
+  if (rc == POMP_OK && needed > 0)
+    CUDA_TRY(cudaMemcpyAsync(idx_h, h->out_idx.p, sizeof(int64_t) * (size_t)needed, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return rc;
+}
+
+POMP_API int pomp_nn_merge_candidates(const int64_t* idx_in, const double* dist_in, int32_t n_shards, int64_t nq,
+                                      int32_t k, int64_t* idx_out, double* dist_out, int32_t* count_out,
+                                      void* stream) {
+  POMP_REQUIRE(idx_in && dist_in && idx_out && dist_out && n_shards >= 1 && nq >= 0, "bad arguments to merge");
+  POMP_REQUIRE(k >= 1 && k <= 128, "k=%d outside 1..128", k);
+  if (nq == 0) return POMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((nq * 32 + 255) / 256);
+  // layout [shard][query][k]
+#define MK(KL)                                                                                              \
+  LAUNCH((merge_lists_kernel<KL, int64_t>), blocks, 256, 0, st, dist_in, idx_in, n_shards, (long long)nq, k, \
+         (long long)k, (long long)nq * k, idx_out, dist_out, count_out)
+  if (k <= 32) MK(1);
+  else if (k <= 64) MK(2);
+  else MK(4);
+#undef MK
+  CHECK_LAUNCH();
+  return POMP_OK;
+}

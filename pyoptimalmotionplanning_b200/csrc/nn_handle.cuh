@@ -1,0 +1,76 @@
+// nn_handle.cuh -- the NearestNeighbors handle (shared by nn.cu and the fused extend kernel).
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "grid.cuh"
+
+using namespace pomp;
+
+// ============================================================================ handle
+struct pomp_nn {
+  int device = 0;
+  pomp_metric_desc metric;
+  int D = 0;
+  // canonical store, insertion order
+  double* d_pts = nullptr;
+  uint8_t* d_skip = nullptr;  // dead | rejected, zero-filled up to cap
+  int64_t cap = 0;
+  int64_t n_dev = 0;  // points resident on the device
+  std::vector<double> pending;  // host-side adds not yet uploaded
+  std::vector<uint8_t> h_dead;
+  std::vector<uint8_t> h_reject;
+  bool any_dead = false, has_reject = false;
+  // grid index
+  bool grid_valid = false;
+  bool grid_unusable = false;  // metric gives no grid axis
+  GridDev grid;
+  DevBuf<int> cell_start;
+  DevBuf<double> spts;
+  DevBuf<int> sidx;
+  DevBuf<int> tmp_i32;  // slot per point / counts
+  DevBuf<long long> scan_tmp;
+  // knobs
+  double grid_min_points = 16384;
+  double points_per_cell = 0;  // 0 = auto by number of grid axes
+  double sort_queries = 1;
+  double grid_min_queries = 64;
+  double max_tail = 2048;
+  // scratch for queries
+  DevBuf<double> q_dev;
+  DevBuf<double> part_d;
+  DevBuf<int> part_i;
+  DevBuf<int> counts;
+  DevBuf<int> qperm;
+  DevBuf<int> qcell;
+  DevBuf<int64_t> out_idx;
+  DevBuf<double> out_dist;
+  DevBuf<int32_t> out_cnt;
+  DevBuf<int64_t> out_off;
+  // pinned mailbox for the single-query fast path
+  void* mailbox_h = nullptr;
+  void* mailbox_d = nullptr;
+  unsigned int* ticket = nullptr;
+  cudaStream_t stream = nullptr;  // used by the *_h variants
+
+  int64_t size() const { return n_dev + (int64_t)(pending.size() / (size_t)std::max(D, 1)); }
+  const uint8_t* skip_ptr() const { return (any_dead || has_reject) ? d_skip : nullptr; }
+};
+
+
+namespace pomp {
+int nn_grow(pomp_nn* h, int64_t need, cudaStream_t st);
+int nn_flush(pomp_nn* h, cudaStream_t st);
+
+struct QueryArg {
+  double v[POMP_MAX_DIM];
+};
+struct Mailbox {
+  int64_t idx;
+  double dist;
+  int64_t aux[6];
+  double x[POMP_MAX_DIM];
+  double len;
+};
+}  // namespace pomp

@@ -1,0 +1,576 @@
+// space.cu -- ConfigurationSpace.feasible and EpsilonEdgeChecker.feasible on the device.
+//
+// EpsilonEdgeChecker (pomp/spaces/edgechecker.py:20-30) is a SAMPLED check, not a swept one:
+// l = length(); k = ceil(l/res); endpoints first; then eval((i+1)/(k+2)) for i in [0,k).  The
+// kernels reproduce that schedule exactly (one edge per thread, early exit on the first
+// infeasible sample), so booleans match the reference even where a swept test would differ.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "dyn.cuh"
+#include "space.cuh"
+
+using namespace pomp;
+
+// ============================================================================ kernels
+__global__ void feasible_kernel(SpaceDev s, const double* __restrict__ x, long long n, uint8_t* __restrict__ ok) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[POMP_MAX_DIM];
+  for (int j = 0; j < s.dim; j++) p[j] = x[i * s.dim + j];
+  ok[i] = feasible_pt(s, p) ? 1 : 0;
+}
+
+// LinearInterpolator edge a->b (interpolators.py:28-33): length = vectorops.distance,
+// eval(u) = a + u*(b-a) (vectorops.py:14-18,115-117)
+template <int D>
+__device__ __forceinline__ bool edge_linear(const SpaceDev& s, const double* a, const double* b, double res) {
+  constexpr int DA = D ? D : POMP_MAX_DIM;
+  const int dim = D ? D : s.dim;
+  double l = 0.0;
+#pragma unroll
+  for (int j = 0; j < DA; j++)
+    if (j < dim) {
+      double t = a[j] - b[j];
+      l = l + t * t;
+    }
+  l = sqrt(l);
+  long long k = edge_samples(l, res);
+  if (!feasible_pt(s, a) || !feasible_pt(s, b)) return false;
+  double dlt[DA];
+#pragma unroll
+  for (int j = 0; j < DA; j++) dlt[j] = j < dim ? b[j] - a[j] : 0.0;
+  const double kk2 = (double)(k + 2);
+  for (long long i = 0; i < k; i++) {
+    double u = (double)(i + 1) / kk2;
+    double x[DA];
+#pragma unroll
+    for (int j = 0; j < DA; j++) x[j] = j < dim ? a[j] + u * dlt[j] : 0.0;
+    if (!feasible_pt(s, x)) return false;
+  }
+  return true;
+}
+
+template <int D>
+__global__ void edge_check_kernel(SpaceDev s, const double* __restrict__ a, const double* __restrict__ b,
+                                  long long n, double res, uint8_t* __restrict__ ok) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int DA = D ? D : POMP_MAX_DIM;
+  const int dim = D ? D : s.dim;
+  double pa[DA], pb[DA];
+  if (D == 2) {
+    double2 va = __ldg(reinterpret_cast<const double2*>(a) + i);
+    double2 vb = __ldg(reinterpret_cast<const double2*>(b) + i);
+    pa[0] = va.x;
+    pa[1] = va.y;
+    pb[0] = vb.x;
+    pb[1] = vb.y;
+  } else {
+    for (int j = 0; j < dim; j++) {
+      pa[j] = a[i * dim + j];
+      pb[j] = b[i * dim + j];
+    }
+  }
+  ok[i] = edge_linear<D>(s, pa, pb, res) ? 1 : 0;
+}
+
+template <int D>
+__global__ void edge_check_indexed_kernel(SpaceDev s, const double* __restrict__ nodes, const int* __restrict__ ij,
+                                          long long n, double res, uint8_t* __restrict__ ok) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  constexpr int DA = D ? D : POMP_MAX_DIM;
+  const int dim = D ? D : s.dim;
+  int2 pr = __ldg(reinterpret_cast<const int2*>(ij) + e);
+  double pa[DA], pb[DA];
+  for (int j = 0; j < dim; j++) {
+    pa[j] = __ldg(nodes + (long long)pr.x * dim + j);
+    pb[j] = __ldg(nodes + (long long)pr.y * dim + j);
+  }
+  ok[e] = edge_linear<D>(s, pa, pb, res) ? 1 : 0;
+}
+
+// PiecewiseLinearInterpolator (interpolators.py:73-102) over explicit waypoints
+__global__ void edge_check_path_kernel(SpaceDev s, pomp_metric_desc g, const double* __restrict__ wp,
+                                       const int* __restrict__ off, long long n_paths, double res,
+                                       uint8_t* __restrict__ ok) {
+  long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pi >= n_paths) return;
+  const int D = s.dim;
+  const double* P = wp + (long long)off[pi] * D;
+  int np = off[pi + 1] - off[pi];
+  if (np <= 0) {
+    ok[pi] = 0;
+    return;
+  }
+  double a[POMP_MAX_DIM], b[POMP_MAX_DIM], x[POMP_MAX_DIM];
+  double l = 0.0;  // l = 0; l += distance(path[i], path[i+1])  (:88-92)
+  for (int j = 0; j < D; j++) a[j] = P[j];
+  for (int i = 0; i + 1 < np; i++) {
+    for (int j = 0; j < D; j++) b[j] = P[(long long)(i + 1) * D + j];
+    l += metric_eval(g, a, b);
+    for (int j = 0; j < D; j++) a[j] = b[j];
+  }
+  long long k = edge_samples(l, res);
+  for (int j = 0; j < D; j++) {
+    a[j] = P[j];
+    b[j] = P[(long long)(np - 1) * D + j];
+  }
+  if (!feasible_pt(s, a) || !feasible_pt(s, b)) {
+    ok[pi] = 0;
+    return;
+  }
+  const double kk2 = (double)(k + 2);
+  for (long long i = 0; i < k; i++) {
+    double u = (double)(i + 1) / kk2;
+    // eval(u) (:93-102); u is strictly inside (0,1) here
+    double kk = u * (double)(np - 1);
+    double fl = floor(kk);
+    double sfrac = kk - fl;
+    long long seg = (long long)fl;
+    for (int j = 0; j < D; j++) {
+      a[j] = P[seg * D + j];
+      b[j] = P[(seg + 1) * D + j];
+    }
+    geodesic_interp(g, a, b, sfrac, D, x);
+    if (!feasible_pt(s, x)) {
+      ok[pi] = 0;
+      return;
+    }
+  }
+  ok[pi] = 1;
+}
+
+// controlSpace.interpolator(x,u) + EpsilonEdgeChecker without materialising the curve
+__global__ void edge_check_control_kernel(SpaceDev s, pomp_dyn_desc dy, pomp_metric_desc g,
+                                          const double* __restrict__ xs, const double* __restrict__ us, long long n,
+                                          double res, uint8_t* __restrict__ ok) {
+  long long ei = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ei >= n) return;
+  const int X = dy.x_dim, U = dy.u_dim;
+  double x[POMP_MAX_DIM], u[POMP_MAX_DIM], cur[POMP_MAX_DIM], nxt[POMP_MAX_DIM], pt[POMP_MAX_DIM];
+  for (int j = 0; j < X; j++) x[j] = xs[ei * X + j];
+  for (int j = 0; j < U; j++) u[j] = us[ei * U + j];
+  if (dy.kind == POMP_DYN_ADAPTOR) {
+    ok[ei] = edge_linear<0>(s, x, u, res) ? 1 : 0;
+    return;
+  }
+  if (dy.kind == POMP_DYN_DUBINS) {  // DubinsCarInterpolator (dubins.py:62-73)
+    dubins_next(x, u[0], u[1], nxt);
+    long long k = edge_samples(fabs(u[0]), res);
+    bool good = feasible_pt(s, x) && feasible_pt(s, nxt);
+    const double kk2 = (double)(k + 2);
+    for (long long i = 0; good && i < k; i++) {
+      double uu = (double)(i + 1) / kk2;
+      dubins_next(x, u[0] * uu, u[1], pt);
+      good = feasible_pt(s, pt);
+    }
+    ok[ei] = good ? 1 : 0;
+    return;
+  }
+  // integrated kinds: pass 1 = waypoint count + geodesic length
+  double duration = u[0];
+  double dt0 = euler_dt0(dy, duration);
+  long long np = 1;
+  double l = 0.0, t = 0.0;
+  for (int j = 0; j < X; j++) cur[j] = x[j];
+  while (t < duration) {
+    double dt = fmin(dt0, duration - t);
+    euler_step(dy, cur, u, dt, nxt);
+    l += metric_eval(g, cur, nxt);
+    for (int j = 0; j < X; j++) cur[j] = nxt[j];
+    np++;
+    t = fmin(t + dt0, duration);
+  }
+  long long k = edge_samples(l, res);
+  if (!feasible_pt(s, x) || !feasible_pt(s, cur)) {
+    ok[ei] = 0;
+    return;
+  }
+  // pass 2: samples are increasing in u, so one more forward sweep serves them all
+  long long seg_cur = 0;
+  t = 0.0;
+  for (int j = 0; j < X; j++) cur[j] = x[j];
+  if (np > 1) {
+    double dt = fmin(dt0, duration - t);
+    euler_step(dy, cur, u, dt, nxt);
+    t = fmin(t + dt0, duration);
+  }
+  const double kk2 = (double)(k + 2);
+  for (long long i = 0; i < k; i++) {
+    double uu = (double)(i + 1) / kk2;
+    double kk = uu * (double)(np - 1);
+    double fl = floor(kk);
+    double sfrac = kk - fl;
+    long long seg = (long long)fl;
+    while (seg_cur < seg) {  // advance [cur,nxt] to waypoints [seg, seg+1]
+      for (int j = 0; j < X; j++) cur[j] = nxt[j];
+      double dt = fmin(dt0, duration - t);
+      euler_step(dy, cur, u, dt, nxt);
+      t = fmin(t + dt0, duration);
+      seg_cur++;
+    }
+    geodesic_interp(g, cur, nxt, sfrac, X, pt);
+    if (!feasible_pt(s, pt)) {
+      ok[ei] = 0;
+      return;
+    }
+  }
+  ok[ei] = 1;
+}
+
+// ============================================================================ host: space handle
+static int build_obstacle_grid(pomp_space* sp, const pomp_space_desc* d, cudaStream_t st) {
+  SpaceDev& s = sp->dev;
+  int nb = d->n_boxes, nc = d->n_circles, no = nb + nc;
+  s.use_grid = 0;
+  if (no <= 16) return POMP_OK;  // a handful of obstacles: the plain loop is faster
+  std::vector<double> ox0(no), oy0(no), ox1(no), oy1(no);
+  for (int o = 0; o < nb; o++) {
+    const double* b = d->boxes_h + 4 * o;
+    ox0[o] = b[0];
+    oy0[o] = b[1];
+    ox1[o] = b[2];
+    oy1[o] = b[3];
+  }
+  for (int o = 0; o < nc; o++) {
+    const double* c = d->circles_h + 3 * o;
+    double sl = 1e-9 * (fabs(c[0]) + fabs(c[1]) + fabs(c[2])) + 1e-300;
+    ox0[nb + o] = c[0] - c[2] - sl;
+    ox1[nb + o] = c[0] + c[2] + sl;
+    oy0[nb + o] = c[1] - c[2] - sl;
+    oy1[nb + o] = c[1] + c[2] + sl;
+  }
+  double glo0 = INFINITY, glo1 = INFINITY, ghi0 = -INFINITY, ghi1 = -INFINITY;
+  for (int o = 0; o < no; o++) {
+    if (!(ox0[o] <= ox1[o]) || !(oy0[o] <= oy1[o])) continue;  // empty / NaN obstacle: never contains a non-NaN point
+    glo0 = fmin(glo0, ox0[o]);
+    ghi0 = fmax(ghi0, ox1[o]);
+    glo1 = fmin(glo1, oy0[o]);
+    ghi1 = fmax(ghi1, oy1[o]);
+  }
+  if (!(isfinite(glo0) && isfinite(ghi0) && isfinite(glo1) && isfinite(ghi1))) return POMP_OK;
+  double e0 = ghi0 - glo0, e1 = ghi1 - glo1;
+  if (!(e0 > 0.0) || !(e1 > 0.0)) return POMP_OK;
+  int res = (int)ceil(sqrt(4.0 * no));
+  res = std::max(4, std::min(res, 4096));
+  std::vector<int> start, items;
+  int gnx = 0, gny = 0;
+  double inv0 = 0, inv1 = 0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    gnx = gny = res;
+    inv0 = (double)gnx / e0;
+    inv1 = (double)gny / e1;
+    std::vector<int> cnt((size_t)gnx * gny + 1, 0);
+    long long total = 0;
+    for (int o = 0; o < no; o++) {
+      if (!(ox0[o] <= ox1[o]) || !(oy0[o] <= oy1[o])) continue;
+      int cx0 = obs_cell(ox0[o], glo0, inv0, gnx), cx1 = obs_cell(ox1[o], glo0, inv0, gnx);
+      int cy0 = obs_cell(oy0[o], glo1, inv1, gny), cy1 = obs_cell(oy1[o], glo1, inv1, gny);
+      for (int cy = cy0; cy <= cy1; cy++)
+        for (int cx = cx0; cx <= cx1; cx++) cnt[(size_t)cy * gnx + cx]++;
+      total += (long long)(cx1 - cx0 + 1) * (cy1 - cy0 + 1);
+    }
+    if (total > 64LL * no && res > 4) {  // obstacles much larger than cells: coarsen
+      res = std::max(4, res / 2);
+      continue;
+    }
+    start.assign((size_t)gnx * gny + 1, 0);
+    for (size_t c = 0; c < (size_t)gnx * gny; c++) start[c + 1] = start[c] + cnt[c];
+    items.assign((size_t)std::max<long long>(total, 1), 0);
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (int o = 0; o < no; o++) {
+      if (!(ox0[o] <= ox1[o]) || !(oy0[o] <= oy1[o])) continue;
+      int cx0 = obs_cell(ox0[o], glo0, inv0, gnx), cx1 = obs_cell(ox1[o], glo0, inv0, gnx);
+      int cy0 = obs_cell(oy0[o], glo1, inv1, gny), cy1 = obs_cell(oy1[o], glo1, inv1, gny);
+      for (int cy = cy0; cy <= cy1; cy++)
+        for (int cx = cx0; cx <= cx1; cx++) items[(size_t)fill[(size_t)cy * gnx + cx]++] = o;
+    }
+    break;
+  }
+  if (start.empty()) return POMP_OK;
+  CUDA_TRY(cudaMalloc((void**)&sp->d_cell_start, sizeof(int) * start.size()));
+  CUDA_TRY(cudaMalloc((void**)&sp->d_cell_items, sizeof(int) * items.size()));
+  CUDA_TRY(cudaMemcpyAsync(sp->d_cell_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(sp->d_cell_items, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  s.use_grid = 1;
+  s.gnx = gnx;
+  s.gny = gny;
+  s.glo0 = glo0;
+  s.glo1 = glo1;
+  s.ghi0 = ghi0;
+  s.ghi1 = ghi1;
+  s.ginv0 = inv0;
+  s.ginv1 = inv1;
+  s.cell_start = sp->d_cell_start;
+  s.cell_items = sp->d_cell_items;
+  return POMP_OK;
+}
+
+POMP_API int pomp_space_create(const pomp_space_desc* d, int device, pomp_space** out) {
+  POMP_REQUIRE(out != nullptr && d != nullptr, "NULL argument to pomp_space_create");
+  *out = nullptr;
+  POMP_REQUIRE(d->dim >= 1 && d->dim <= POMP_MAX_DIM, "space dim %d outside 1..%d", d->dim, POMP_MAX_DIM);
+  POMP_REQUIRE(d->n_boxes >= 0 && d->n_circles >= 0, "negative obstacle count");
+  POMP_REQUIRE(d->n_boxes == 0 || d->boxes_h, "boxes_h is NULL");
+  POMP_REQUIRE(d->n_circles == 0 || d->circles_h, "circles_h is NULL");
+  if (d->n_boxes + d->n_circles > 0)
+    POMP_REQUIRE(d->obstacle_dim0 >= 0 && d->obstacle_dim0 < d->dim && d->obstacle_dim1 >= 0 &&
+                     d->obstacle_dim1 < d->dim,
+                 "obstacle dims (%d,%d) outside the space", d->obstacle_dim0, d->obstacle_dim1);
+  DeviceGuard g(device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  pomp_space* sp = new pomp_space();
+  sp->device = device;
+  SpaceDev& s = sp->dev;
+  memset(&s, 0, sizeof(s));
+  s.dim = d->dim;
+  s.od0 = d->n_boxes + d->n_circles > 0 ? d->obstacle_dim0 : 0;
+  s.od1 = d->n_boxes + d->n_circles > 0 ? d->obstacle_dim1 : 0;
+  s.n_boxes = d->n_boxes;
+  s.n_circles = d->n_circles;
+  for (int i = 0; i < d->dim; i++) {
+    s.lo[i] = d->lo[i];
+    s.hi[i] = d->hi[i];
+  }
+  auto fail = [&](int rc) {
+    pomp_space_destroy(sp);
+    return rc;
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&sp->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+    return fail(POMP_ERR_CUDA);
+  }
+  if (d->n_boxes) {
+    if (cudaMalloc((void**)&sp->d_boxes, sizeof(double) * 4 * d->n_boxes) != cudaSuccess ||
+        cudaMemcpy(sp->d_boxes, d->boxes_h, sizeof(double) * 4 * d->n_boxes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("uploading boxes failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return fail(POMP_ERR_CUDA);
+    }
+  }
+  if (d->n_circles) {
+    if (cudaMalloc((void**)&sp->d_circles, sizeof(double) * 3 * d->n_circles) != cudaSuccess ||
+        cudaMemcpy(sp->d_circles, d->circles_h, sizeof(double) * 3 * d->n_circles, cudaMemcpyHostToDevice) !=
+            cudaSuccess) {
+      set_error("uploading circles failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return fail(POMP_ERR_CUDA);
+    }
+  }
+  s.boxes = sp->d_boxes;
+  s.circles = sp->d_circles;
+  int rc = build_obstacle_grid(sp, d, sp->stream);
+  if (rc != POMP_OK) return fail(rc);
+  *out = sp;
+  return POMP_OK;
+}
+
+POMP_API int pomp_space_destroy(pomp_space* sp) {
+  if (!sp) return POMP_OK;
+  DeviceGuard g(sp->device);
+  if (sp->d_boxes) cudaFree(sp->d_boxes);
+  if (sp->d_circles) cudaFree(sp->d_circles);
+  if (sp->d_cell_start) cudaFree(sp->d_cell_start);
+  if (sp->d_cell_items) cudaFree(sp->d_cell_items);
+  if (sp->stream) cudaStreamDestroy(sp->stream);
+  delete sp;
+  return POMP_OK;
+}
+
+POMP_API int pomp_space_set_bounds(pomp_space* sp, const double* lo_h, const double* hi_h) {
+  POMP_REQUIRE(sp && lo_h && hi_h, "NULL argument to pomp_space_set_bounds");
+  for (int i = 0; i < sp->dev.dim; i++) {
+    sp->dev.lo[i] = lo_h[i];
+    sp->dev.hi[i] = hi_h[i];
+  }
+  return POMP_OK;
+}
+
+// ---- device entry points -------------------------------------------------------------------
+POMP_API int pomp_feasible(pomp_space* sp, const double* x, int64_t n, uint8_t* ok, void* stream) {
+  POMP_REQUIRE(sp && (n == 0 || (x && ok)) && n >= 0, "bad arguments to pomp_feasible");
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n == 0) return POMP_OK;
+  LAUNCH(feasible_kernel, (int)((n + 255) / 256), 256, 0, (cudaStream_t)stream, sp->dev, x, (long long)n, ok);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+POMP_API int pomp_edge_check(pomp_space* sp, const double* a, const double* b, int64_t n, double resolution,
+                             uint8_t* ok, void* stream) {
+  POMP_REQUIRE(sp && (n == 0 || (a && b && ok)) && n >= 0, "bad arguments to pomp_edge_check");
+  POMP_REQUIRE(resolution > 0.0, "resolution must be positive");
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n == 0) return POMP_OK;
+  int blocks = (int)((n + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sp->dev.dim == 2) LAUNCH((edge_check_kernel<2>), blocks, 128, 0, st, sp->dev, a, b, (long long)n, resolution, ok);
+  else LAUNCH((edge_check_kernel<0>), blocks, 128, 0, st, sp->dev, a, b, (long long)n, resolution, ok);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+POMP_API int pomp_edge_check_indexed(pomp_space* sp, const double* nodes, const int32_t* ij, int64_t n_edges,
+                                     double resolution, uint8_t* ok, void* stream) {
+  POMP_REQUIRE(sp && (n_edges == 0 || (nodes && ij && ok)) && n_edges >= 0, "bad arguments to pomp_edge_check_indexed");
+  POMP_REQUIRE(resolution > 0.0, "resolution must be positive");
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n_edges == 0) return POMP_OK;
+  int blocks = (int)((n_edges + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sp->dev.dim == 2)
+    LAUNCH((edge_check_indexed_kernel<2>), blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok);
+  else
+    LAUNCH((edge_check_indexed_kernel<0>), blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+static int validate_geodesic(const pomp_metric_desc* g, int dim) {
+  POMP_REQUIRE(g != nullptr, "geodesic descriptor is NULL");
+  POMP_REQUIRE(!g->has_cost, "geodesic descriptor must not carry a cost coordinate");
+  POMP_REQUIRE(g->dim == dim, "geodesic dim %d != space dim %d", g->dim, dim);
+  POMP_REQUIRE(g->kind == POMP_METRIC_EUCLIDEAN || g->kind == POMP_METRIC_GEODESIC_PRODUCT,
+               "geodesic must be EUCLIDEAN or GEODESIC_PRODUCT");
+  return POMP_OK;
+}
+
+POMP_API int pomp_edge_check_path(pomp_space* sp, const pomp_metric_desc* geodesic, const double* waypoints,
+                                  const int32_t* path_offsets, int64_t n_paths, double resolution, uint8_t* ok,
+                                  void* stream) {
+  POMP_REQUIRE(sp && (n_paths == 0 || (waypoints && path_offsets && ok)) && n_paths >= 0,
+               "bad arguments to pomp_edge_check_path");
+  POMP_REQUIRE(resolution > 0.0, "resolution must be positive");
+  POMP_TRY(validate_geodesic(geodesic, sp->dev.dim));
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n_paths == 0) return POMP_OK;
+  LAUNCH(edge_check_path_kernel, (int)((n_paths + 63) / 64), 64, 0, (cudaStream_t)stream, sp->dev, *geodesic,
+         waypoints, path_offsets, (long long)n_paths, resolution, ok);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+int pomp::validate_dyn(const pomp_dyn_desc* d) {
+  POMP_REQUIRE(d != nullptr, "dynamics descriptor is NULL");
+  POMP_REQUIRE(d->kind >= 0 && d->kind <= POMP_DYN_FLAPPY, "unknown dynamics kind %d", d->kind);
+  POMP_REQUIRE(d->x_dim >= 1 && d->x_dim + (d->cost_kind != POMP_COST_NONE) <= POMP_MAX_DIM, "bad x_dim %d", d->x_dim);
+  POMP_REQUIRE(d->u_dim >= 1 && d->u_dim <= POMP_MAX_DIM, "bad u_dim %d", d->u_dim);
+  POMP_REQUIRE(d->cost_kind >= 0 && d->cost_kind <= POMP_COST_PATH_LENGTH, "unknown cost kind %d", d->cost_kind);
+  if (d->kind == POMP_DYN_CV || d->kind == POMP_DYN_CV_EULER)
+    POMP_REQUIRE(d->x_dim % 2 == 0 && d->u_dim == d->x_dim / 2 + 1, "CV dynamics need x=(q,v), u=(dt,a)");
+  if (d->kind == POMP_DYN_CV_EULER || d->kind == POMP_DYN_PENDULUM)
+    POMP_REQUIRE(d->dt > 0.0, "integration step dt must be positive");
+  if (d->kind == POMP_DYN_DUBINS) POMP_REQUIRE(d->x_dim == 3 && d->u_dim == 2, "Dubins needs x_dim=3, u_dim=2");
+  if (d->kind == POMP_DYN_PENDULUM) POMP_REQUIRE(d->x_dim == 2 && d->u_dim == 2, "Pendulum needs x_dim=2, u_dim=2");
+  if (d->kind == POMP_DYN_FLAPPY) POMP_REQUIRE(d->x_dim == 3 && d->u_dim == 2, "Flappy needs x_dim=3, u_dim=2");
+  if (d->kind == POMP_DYN_ADAPTOR) POMP_REQUIRE(d->u_dim == d->x_dim, "adaptor needs u_dim == x_dim");
+  if (d->cost_kind == POMP_COST_PATH_LENGTH) POMP_REQUIRE(d->kind == POMP_DYN_ADAPTOR, "path-length cost needs an adaptor");
+  return POMP_OK;
+}
+
+POMP_API int pomp_edge_check_control(pomp_space* sp, const pomp_dyn_desc* dyn, const pomp_metric_desc* geodesic,
+                                     const double* x, const double* u, int64_t n, double resolution, uint8_t* ok,
+                                     void* stream) {
+  POMP_REQUIRE(sp && (n == 0 || (x && u && ok)) && n >= 0, "bad arguments to pomp_edge_check_control");
+  POMP_REQUIRE(resolution > 0.0, "resolution must be positive");
+  POMP_TRY(validate_dyn(dyn));
+  POMP_REQUIRE(dyn->x_dim == sp->dev.dim, "dynamics x_dim %d != space dim %d", dyn->x_dim, sp->dev.dim);
+  POMP_REQUIRE(dyn->kind == POMP_DYN_ADAPTOR || dyn->kind == POMP_DYN_DUBINS || dyn->kind == POMP_DYN_PENDULUM ||
+                   dyn->kind == POMP_DYN_CV_EULER,
+               "edge_check_control supports ADAPTOR, DUBINS, PENDULUM, CV_EULER");
+  pomp_metric_desc gd;
+  memset(&gd, 0, sizeof(gd));
+  gd.kind = POMP_METRIC_EUCLIDEAN;
+  gd.dim = sp->dev.dim;
+  if (dyn->kind == POMP_DYN_PENDULUM || dyn->kind == POMP_DYN_CV_EULER) {
+    POMP_TRY(validate_geodesic(geodesic, sp->dev.dim));
+    gd = *geodesic;
+  }
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n == 0) return POMP_OK;
+  LAUNCH(edge_check_control_kernel, (int)((n + 63) / 64), 64, 0, (cudaStream_t)stream, sp->dev, *dyn, gd, x, u,
+         (long long)n, resolution, ok);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+// ---- host-buffer variants ------------------------------------------------------------------
+#define H2D(buf, src, count, T)                                                                       \
+  do {                                                                                                \
+    POMP_TRY(buf.reserve((size_t)(count)));                                                           \
+    CUDA_TRY(cudaMemcpyAsync(buf.p, src, sizeof(T) * (size_t)(count), cudaMemcpyHostToDevice, st));   \
+  } while (0)
+
+static int finish_ok(pomp_space* sp, uint8_t* ok_h, int64_t n, cudaStream_t st) {
+  CUDA_TRY(cudaMemcpyAsync(ok_h, sp->out_ok.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return POMP_OK;
+}
+
+POMP_API int pomp_feasible_h(pomp_space* sp, const double* x_h, int64_t n, uint8_t* ok_h) {
+  POMP_REQUIRE(sp && (n == 0 || (x_h && ok_h)) && n >= 0, "bad arguments to pomp_feasible_h");
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n == 0) return POMP_OK;
+  cudaStream_t st = sp->stream;
+  H2D(sp->in_a, x_h, n * sp->dev.dim, double);
+  POMP_TRY(sp->out_ok.reserve((size_t)n));
+  POMP_TRY(pomp_feasible(sp, sp->in_a.p, n, sp->out_ok.p, st));
+  return finish_ok(sp, ok_h, n, st);
+}
+
+POMP_API int pomp_edge_check_h(pomp_space* sp, const double* a_h, const double* b_h, int64_t n, double resolution,
+                               uint8_t* ok_h) {
+  POMP_REQUIRE(sp && (n == 0 || (a_h && b_h && ok_h)) && n >= 0, "bad arguments to pomp_edge_check_h");
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n == 0) return POMP_OK;
+  cudaStream_t st = sp->stream;
+  H2D(sp->in_a, a_h, n * sp->dev.dim, double);
+  H2D(sp->in_b, b_h, n * sp->dev.dim, double);
+  POMP_TRY(sp->out_ok.reserve((size_t)n));
+  POMP_TRY(pomp_edge_check(sp, sp->in_a.p, sp->in_b.p, n, resolution, sp->out_ok.p, st));
+  return finish_ok(sp, ok_h, n, st);
+}
+
+POMP_API int pomp_edge_check_path_h(pomp_space* sp, const pomp_metric_desc* geodesic, const double* waypoints_h,
+                                    const int32_t* path_offsets_h, int64_t n_paths, double resolution,
+                                    uint8_t* ok_h) {
+  POMP_REQUIRE(sp && (n_paths == 0 || (waypoints_h && path_offsets_h && ok_h)) && n_paths >= 0,
+               "bad arguments to pomp_edge_check_path_h");
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n_paths == 0) return POMP_OK;
+  cudaStream_t st = sp->stream;
+  int64_t nw = path_offsets_h[n_paths];
+  POMP_REQUIRE(nw >= 0, "negative waypoint count");
+  H2D(sp->in_a, waypoints_h, std::max<int64_t>(nw, 1) * sp->dev.dim, double);
+  H2D(sp->in_i, path_offsets_h, n_paths + 1, int32_t);
+  POMP_TRY(sp->out_ok.reserve((size_t)n_paths));
+  POMP_TRY(pomp_edge_check_path(sp, geodesic, sp->in_a.p, sp->in_i.p, n_paths, resolution, sp->out_ok.p, st));
+  return finish_ok(sp, ok_h, n_paths, st);
+}
+
+POMP_API int pomp_edge_check_control_h(pomp_space* sp, const pomp_dyn_desc* dyn, const pomp_metric_desc* geodesic,
+                                       const double* x_h, const double* u_h, int64_t n, double resolution,
+                                       uint8_t* ok_h) {
+  POMP_REQUIRE(sp && dyn && (n == 0 || (x_h && u_h && ok_h)) && n >= 0, "bad arguments to pomp_edge_check_control_h");
+  POMP_TRY(validate_dyn(dyn));
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n == 0) return POMP_OK;
+  cudaStream_t st = sp->stream;
+  H2D(sp->in_a, x_h, n * dyn->x_dim, double);
+  H2D(sp->in_b, u_h, n * dyn->u_dim, double);
+  POMP_TRY(sp->out_ok.reserve((size_t)n));
+  POMP_TRY(pomp_edge_check_control(sp, dyn, geodesic, sp->in_a.p, sp->in_b.p, n, resolution, sp->out_ok.p, st));
+  return finish_ok(sp, ok_h, n, st);
+}

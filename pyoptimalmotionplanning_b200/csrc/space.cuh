@@ -1,0 +1,100 @@
+// space.cuh -- device-side feasibility test shared by the feasibility, edge-check, propagation and
+// fused extend kernels.
+//
+// Semantics (reference): BoxSet.contains (pomp/spaces/sets.py:177-182) on every coordinate,
+// then "outside every obstacle" (example_problems/geometric.py:56-60) with closed boxes and
+// closed discs (geometric.py:15-16).  NaN coordinates follow the Python comparisons: they pass a
+// box test and fail a disc test.
+//
+// Obstacles are bucketed into a uniform 2-D grid built on the host with the SAME monotone cell
+// function the device uses, so the grid only prunes candidates and never changes a boolean.
+#pragma once
+#include "common.cuh"
+
+namespace pomp {
+
+struct SpaceDev {
+  int dim, od0, od1, n_boxes, n_circles;
+  int use_grid, gnx, gny;
+  double lo[POMP_MAX_DIM], hi[POMP_MAX_DIM];
+  double glo0, glo1, ghi0, ghi1, ginv0, ginv1;  // obstacle grid domain = bounding box of all obstacles
+  const double* boxes;    // n_boxes x 4
+  const double* circles;  // n_circles x 3
+  const int* cell_start;  // gnx*gny + 1
+  const int* cell_items;  // obstacle ids: boxes first, then n_boxes + circle id
+};
+
+__host__ __device__ __forceinline__ int obs_cell(double x, double lo, double inv, int n) {
+  double t = (x - lo) * inv;
+  if (t >= (double)n) return n - 1;
+  return t > 0.0 ? (int)t : 0;
+}
+
+__device__ __forceinline__ bool in_box(const double* __restrict__ b, double px, double py) {
+  // BoxSet.contains: outside iff (xi < a or xi > b) on some coordinate
+  if (px < b[0] || px > b[2]) return false;
+  if (py < b[1] || py > b[3]) return false;
+  return true;
+}
+
+__device__ __forceinline__ bool in_circle(const double* __restrict__ c, double px, double py) {
+  double dx = px - c[0], dy = py - c[1];
+  double s = 0.0;
+  s = s + dx * dx;
+  s = s + dy * dy;
+  return sqrt(s) <= c[2];
+}
+
+__device__ __forceinline__ bool hits_obstacle(const SpaceDev& s, double px, double py) {
+  if (s.n_boxes + s.n_circles == 0) return false;
+  bool use_grid = s.use_grid && !(isnan(px) || isnan(py));
+  if (!use_grid) {
+    for (int o = 0; o < s.n_boxes; o++)
+      if (in_box(s.boxes + 4 * o, px, py)) return true;
+    for (int o = 0; o < s.n_circles; o++)
+      if (in_circle(s.circles + 3 * o, px, py)) return true;
+    return false;
+  }
+  if (px < s.glo0 || px > s.ghi0 || py < s.glo1 || py > s.ghi1) return false;  // outside every obstacle's box
+  int cx = obs_cell(px, s.glo0, s.ginv0, s.gnx), cy = obs_cell(py, s.glo1, s.ginv1, s.gny);
+  int c = cy * s.gnx + cx;
+  int b = __ldg(s.cell_start + c), e = __ldg(s.cell_start + c + 1);
+  for (int it = b; it < e; it++) {
+    int o = __ldg(s.cell_items + it);
+    if (o < s.n_boxes) {
+      if (in_box(s.boxes + 4 * o, px, py)) return true;
+    } else if (in_circle(s.circles + 3 * (o - s.n_boxes), px, py)) {
+      return true;
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool feasible_pt(const SpaceDev& s, const double* x) {
+  for (int i = 0; i < s.dim; i++)
+    if (x[i] < s.lo[i] || x[i] > s.hi[i]) return false;
+  return !hits_obstacle(s, x[s.od0], x[s.od1]);
+}
+
+// EpsilonEdgeChecker sample count (edgechecker.py:21-22): k = int(ceil(l / resolution))
+__device__ __forceinline__ long long edge_samples(double l, double res) {
+  double c = ceil(l / res);
+  if (!(c > 0.0)) return 0;
+  if (c > 1e15) return 1000000000000000LL;
+  return (long long)c;
+}
+
+}  // namespace pomp
+
+struct pomp_space {
+  int device = 0;
+  pomp::SpaceDev dev;
+  double* d_boxes = nullptr;
+  double* d_circles = nullptr;
+  int* d_cell_start = nullptr;
+  int* d_cell_items = nullptr;
+  cudaStream_t stream = nullptr;
+  pomp::DevBuf<double> in_a, in_b;
+  pomp::DevBuf<int32_t> in_i;
+  pomp::DevBuf<uint8_t> out_ok;
+};

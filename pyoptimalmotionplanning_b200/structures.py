@@ -1,0 +1,254 @@
+"""Drop-in for pomp.structures.nearestneighbors.NearestNeighbors (nearestneighbors.py:13-141).
+
+Same constructor and the same seven methods; points and payloads are kept BY REFERENCE on the
+host (planners compare `n.x` by value in remove() and expect nearest() to hand back the very
+objects they stored), coordinates live on the GPU in insertion order.
+
+Semantics chosen where the reference's two back ends disagree:
+  * the exact nearest neighbour under the metric is returned (= method 'bruteforce'; the kd-tree
+    is only approximate on SO(2)/cost metrics);
+  * ties: lowest insertion index wins; knearest is ordered by (distance, insertion index);
+    neighbors is ordered by insertion index;
+  * neighbors uses d <= radius, like the reference's default kd-tree back end (kdtree.py:347);
+    set `inclusive_radius = False` for the brute-force back end's d < radius (:139);
+  * nearest() on an empty set returns None (brute-force behaviour, :88-96).
+"""
+from __future__ import print_function
+
+import numpy as np
+
+from .descriptors import MetricSpec, metric_from_pomp
+
+_COMPACT_MIN = 1024
+
+
+def _default_backend(spec, device):
+    from .backend import CudaNN
+    return CudaNN(spec, device)
+
+
+class NearestNeighbors(object):
+    def __init__(self, metric, method="b200", device=0, _backend_factory=None):
+        self.metric = metric
+        self.method = method
+        self.device = device
+        self.inclusive_radius = True
+        self._factory = _backend_factory or _default_backend
+        self._be = None
+        self._sig = None
+        self._dim = metric.dim if isinstance(metric, MetricSpec) else None
+        self._clear_host()
+
+    # ------------------------------------------------------------------ host bookkeeping
+    def _clear_host(self):
+        self._points = []   # insertion index -> point object
+        self._datas = []    # insertion index -> payload
+        self._alive = []
+        self._ndead = 0
+        self._lookup = {}   # tuple(point) -> [indices], insertion order
+
+    def _metric_signature(self):
+        """Cheap fingerprint of the mutable parts of the metric (CostSpaceRRT.updateBestCost mutates
+        costMax / costWeight in place: kinodynamicplanner.py:1059-1077)."""
+        m = self.metric
+        if isinstance(m, MetricSpec):
+            return m.key()
+        sig = [getattr(m, "costWeight", None), getattr(m, "costMax", None)]
+        base = getattr(m, "metric", m)
+        owner = getattr(base, "__self__", None)
+        geo = getattr(owner, "geodesic", None)
+        w = getattr(geo, "componentWeights", None)
+        if w is not None:
+            sig.append(tuple(w))
+        w = getattr(base, "w", None)
+        if w is not None:
+            sig.append(tuple(w) if hasattr(w, "__iter__") else w)
+        return tuple(sig)
+
+    def _ensure_backend(self, dim):
+        if self._be is None:
+            self._dim = dim
+            spec = metric_from_pomp(self.metric, dim)
+            if spec.dim != dim:
+                raise ValueError("metric is %d-dimensional but points have %d coordinates" % (spec.dim, dim))
+            self._be = self._factory(spec, self.device)
+            self._sig = self._metric_signature()
+        return self._be
+
+    def _sync_metric(self):
+        sig = self._metric_signature()
+        if sig != self._sig:
+            self._be.update_metric(metric_from_pomp(self.metric, self._dim))
+            self._sig = sig
+
+    def __len__(self):
+        return len(self._points) - self._ndead
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self):
+        self._clear_host()
+        if self._be is not None:
+            self._be.reset()
+
+    def add(self, point, data=None):
+        """Adds a point with an associated datum."""
+        be = self._ensure_backend(len(point))
+        idx = be.add_one(point)
+        assert idx == len(self._points)
+        self._points.append(point)
+        self._datas.append(data)
+        self._alive.append(True)
+        self._lookup.setdefault(tuple(point), []).append(idx)
+
+    def remove(self, point, data=None):
+        """Removes the first stored entry with p == point (and pd == data when data is given).
+        Returns the number of points removed (0 or 1)."""
+        key = tuple(point)
+        cands = self._lookup.get(key)
+        if cands:
+            for pos, idx in enumerate(cands):
+                if data is None or self._datas[idx] == data:
+                    del cands[pos]
+                    if not cands:
+                        del self._lookup[key]
+                    self._alive[idx] = False
+                    self._ndead += 1
+                    self._be.remove(idx)
+                    self._maybe_compact()
+                    return 1
+        print("NearestNeighbors: unable to remove", point, "does not exist")
+        return 0
+
+    def set(self, points, datas=None):
+        """Sets the point set to a list of points."""
+        points = list(points)
+        if datas is None:
+            datas = [None] * len(points)
+        datas = list(datas)
+        self._clear_host()
+        if self._be is not None:
+            self._be.reset()
+        if not points:
+            return
+        be = self._ensure_backend(len(points[0]))
+        be.set(np.asarray(points, dtype=np.float64))
+        self._points = points
+        self._datas = datas
+        self._alive = [True] * len(points)
+        for i, p in enumerate(points):
+            self._lookup.setdefault(tuple(p), []).append(i)
+
+    def nearest(self, pt, filter=None):
+        """Nearest neighbor lookup, possibly with filter (filter(point,data) == True rejects)."""
+        if self._be is None or len(self) == 0:
+            return None
+        self._sync_metric()
+        idx, _ = self._be.nearest_one(pt)
+        if idx < 0:
+            return None
+        if filter is None or not filter(self._points[idx], self._datas[idx]):
+            return (self._points[idx], self._datas[idx])
+        # the winner was rejected: walk the candidates in (distance, index) order
+        n = len(self._points)
+        k = 8
+        while True:
+            k = min(k, 128, n)
+            ids, _, cnt = self._be.knearest(np.asarray([pt], dtype=np.float64), k)
+            for j in range(int(cnt[0])):
+                i = int(ids[0, j])
+                if not filter(self._points[i], self._datas[i]):
+                    return (self._points[i], self._datas[i])
+            if int(cnt[0]) < k or k >= n:
+                return None
+            if k >= 128:
+                break
+            k *= 4
+        # more than 128 rejected in a row: evaluate the predicate everywhere and mask on the device
+        return self._masked(filter, lambda: self._first(self._be.nearest_one(pt)))
+
+    def knearest(self, pt, k, filter=None):
+        """K-nearest neighbor lookup, possibly with filter.  Sorted by (distance, insertion index)."""
+        if self._be is None or len(self) == 0:
+            return []
+        self._sync_metric()
+        base = None
+        if filter is not None:
+            base = np.zeros(len(self._points), dtype=np.uint8)
+            for i, (p, d) in enumerate(zip(self._points, self._datas)):
+                if self._alive[i] and filter(p, d):
+                    base[i] = 1
+        q = np.asarray([pt], dtype=np.float64)
+        out = []
+        try:
+            if base is not None:
+                self._be.set_mask(base)
+            if k <= 128:
+                ids, _, cnt = self._be.knearest(q, k)
+                return [(self._points[int(i)], self._datas[int(i)]) for i in ids[0, :int(cnt[0])]]
+            # very large k: peel off 128 at a time by masking what was already returned
+            mask = base if base is not None else np.zeros(len(self._points), dtype=np.uint8)
+            while len(out) < k:
+                ids, _, cnt = self._be.knearest(q, min(128, k - len(out)))
+                c = int(cnt[0])
+                if c == 0:
+                    break
+                for i in ids[0, :c]:
+                    out.append((self._points[int(i)], self._datas[int(i)]))
+                    mask[int(i)] = 1
+                self._be.set_mask(mask)
+                base = mask
+        finally:
+            if base is not None:
+                self._be.set_mask(None)
+        return out
+
+    def neighbors(self, pt, radius):
+        """Range query, all points within radius of pt, in insertion order."""
+        if self._be is None or len(self) == 0:
+            return []
+        self._sync_metric()
+        off, ids = self._be.neighbors(np.asarray([pt], dtype=np.float64), radius, self.inclusive_radius)
+        return [(self._points[int(i)], self._datas[int(i)]) for i in ids]
+
+    # ------------------------------------------------------------------ batched extras
+    def nearest_batch(self, queries):
+        """(idx[nq], dist[nq]) for a batch of queries; idx = -1 where nothing is admissible."""
+        self._sync_metric()
+        return self._be.nearest(queries)
+
+    def knearest_batch(self, queries, k):
+        self._sync_metric()
+        return self._be.knearest(queries, k)
+
+    def neighbors_batch(self, queries, radius):
+        """CSR (offsets[nq+1], idx[hits])."""
+        self._sync_metric()
+        return self._be.neighbors(queries, radius, self.inclusive_radius)
+
+    def item(self, index):
+        return (self._points[index], self._datas[index])
+
+    # ------------------------------------------------------------------ helpers
+    def _first(self, res):
+        idx = res[0]
+        return None if idx < 0 else (self._points[idx], self._datas[idx])
+
+    def _masked(self, filter, fn):
+        mask = np.zeros(len(self._points), dtype=np.uint8)
+        for i, (p, d) in enumerate(zip(self._points, self._datas)):
+            if self._alive[i] and filter(p, d):
+                mask[i] = 1
+        self._be.set_mask(mask)
+        try:
+            return fn()
+        finally:
+            self._be.set_mask(None)
+
+    def _maybe_compact(self):
+        n = len(self._points)
+        if n < _COMPACT_MIN or self._ndead * 2 < n:
+            return
+        keep = [i for i in range(n) if self._alive[i]]
+        pts = [self._points[i] for i in keep]
+        datas = [self._datas[i] for i in keep]
+        self.set(pts, datas)

@@ -1,0 +1,303 @@
+"""CUDA path vs the CPU oracle on seeded random inputs, through the C-ABI: bit-exact indices,
+distances and booleans; edge cases the reference's two back ends exercise."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from pyoptimalmotionplanning_b200 import MetricSpec, SpaceSpec, DynamicsSpec, _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _nn(m, pts=None, grid=None):
+    from pyoptimalmotionplanning_b200.backend import CudaNN
+    nn = CudaNN(m, 0)
+    if grid is True:
+        nn.set_param("grid_min_points", 1)
+        nn.set_param("grid_min_queries", 1)
+    elif grid is False:
+        nn.set_param("grid_min_points", 1e18)
+    if pts is not None:
+        nn.set(pts)
+    return nn
+
+
+@pytest.mark.parametrize("D", [2, 3, 4, 6])
+@pytest.mark.parametrize("k", [1, 16])
+def test_grid_knn_matches_oracle(D, k):
+    rng = np.random.default_rng(100 + D)
+    n, nq = 200000, 1500
+    pts = rng.random((n, D))
+    q = np.concatenate([rng.random((nq - 100, D)), rng.random((100, D)) * 1.4 - 0.2])  # some outside the bbox
+    m = MetricSpec.euclidean(D)
+    nn = _nn(m, pts, grid=True)
+    idx, dist, cnt = nn.knearest(q, k)
+    oi, od, oc = oracle.nn_knearest(m, pts, q, k)
+    assert (cnt == oc).all()
+    assert (idx == oi).all()
+    assert (dist == od).all()
+    # the brute-force kernels agree too
+    nb = _nn(m, pts, grid=False)
+    bi, bd, bc = nb.knearest(q[:200], k)
+    assert (bi == oi[:200]).all() and (bd == od[:200]).all()
+
+
+@pytest.mark.parametrize("k", [3, 33, 70, 128])
+def test_k_buckets(k):
+    rng = np.random.default_rng(7)
+    pts = rng.random((5000, 3))
+    q = rng.random((64, 3))
+    m = MetricSpec.euclidean(3)
+    oi, od, oc = oracle.nn_knearest(m, pts, q, k)
+    for grid in (True, False):
+        idx, dist, cnt = _nn(m, pts, grid).knearest(q, k)
+        assert (idx == oi).all() and (dist == od).all() and (cnt == oc).all(), grid
+
+
+def _metrics():
+    return {
+        "se2": MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi]),
+        "pendulum": MetricSpec.geodesic_product([("SO2",), ("R", 1)], [1.0, 1.0]),
+        "cv": MetricSpec.geodesic_product([("R", 2), ("R", 2)], [1.0, 1.0]),
+        "l1": MetricSpec.l1(3),
+        "linf": MetricSpec.linf(3),
+        "weighted": MetricSpec.weighted_euclidean([1.0, 4.0, 0.25]),
+        "scaled": MetricSpec.scaled_euclidean(2, 0.3),
+        "cost_se2": MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi]).with_cost(1.0, 1.5),
+        "cost_euclid": MetricSpec.euclidean(2).with_cost(0.7, None),
+        "cost_off": MetricSpec.euclidean(3).with_cost(None, None),
+    }
+
+
+def _near_tie_ok(m, pts, q, got_idx, want_idx, want_dist):
+    """Metrics that square through libm pow in the reference can flip candidates that are within
+    a couple of ulps of each other; accept those and nothing else."""
+    bad = np.nonzero(got_idx != want_idx)
+    for r, c in zip(*bad):
+        d_got = oracle.metric(m, pts[got_idx[r, c]], q[r])
+        if abs(d_got - want_dist[r, c]) > 4 * np.spacing(want_dist[r, c]):
+            return False
+    return len(bad[0]) <= max(2, got_idx.size // 500)
+
+
+@pytest.mark.parametrize("name", sorted(_metrics()))
+@pytest.mark.parametrize("grid", [True, False], ids=["grid", "brute"])
+def test_general_metrics_match_oracle(name, grid):
+    m = _metrics()[name]
+    rng = np.random.default_rng(hash(name) % 1000)
+    n, nq, k = 30000, 400, 5
+    lo = np.zeros(m.dim)
+    hi = np.ones(m.dim)
+    if name in ("se2", "cost_se2"):
+        hi[2] = 2 * np.pi
+    if name == "pendulum":
+        lo[:] = [-7, -10]
+        hi[:] = [7, 10]
+    if m.has_cost:
+        hi[-1] = 2.0
+    pts = lo + rng.random((n, m.dim)) * (hi - lo)
+    q = lo + rng.random((nq, m.dim)) * (hi - lo)
+    nn = _nn(m, pts, grid)
+    idx, dist, cnt = nn.knearest(q, k)
+    oi, od, oc = oracle.nn_knearest(m, pts, q, k)
+    assert (cnt == oc).all()
+    exact = m.kind not in (_abi.METRIC_WEIGHTED_EUCLIDEAN, _abi.METRIC_GEODESIC_PRODUCT)
+    if exact:
+        assert (idx == oi).all() and (dist == od).all()
+    else:
+        assert _near_tie_ok(m, pts, q, idx, oi, od)
+        np.testing.assert_allclose(dist, od, rtol=1e-14)
+    off, hits = nn.neighbors(q[:100], 0.05 * float(np.max(hi - lo)))
+    ooff, ohits = oracle.nn_neighbors(m, pts, q[:100], 0.05 * float(np.max(hi - lo)), True)
+    if exact:
+        assert (off == ooff).all() and (hits == ohits).all()
+    else:
+        assert abs(int(off[-1]) - int(ooff[-1])) <= 2
+
+
+def test_masks_tombstones_and_tail():
+    rng = np.random.default_rng(3)
+    D = 2
+    m = MetricSpec.euclidean(D)
+    pts = rng.random((60000, D))
+    q = rng.random((800, D))
+    nn = _nn(m, pts[:50000], grid=True)
+    nn.build_index()
+    nn.add(pts[50000:51500])          # unindexed tail (< max_tail)
+    mask = np.zeros(51500, np.uint8)
+    dead = rng.choice(51500, 5000, replace=False)
+    for i in dead[:50]:
+        nn.remove(int(i))
+    mask[dead] = 1
+    rej = np.zeros(51500, np.uint8)
+    rej[dead[50:]] = 1
+    nn.set_mask(rej)
+    idx, dist, cnt = nn.knearest(q, 8)
+    oi, od, oc = oracle.nn_knearest(m, pts[:51500], q, 8, mask)
+    assert (idx == oi).all() and (dist == od).all()
+    nn.add(pts[51500:])               # tail now exceeds max_tail -> rebuild on the next batch
+    nn.set_mask(None)
+    mask2 = np.zeros(60000, np.uint8)
+    mask2[dead[:50]] = 1
+    idx, dist = nn.nearest(q)
+    oi, od = oracle.nn_nearest(m, pts, q, mask2)
+    assert (idx == oi).all() and (dist == od).all()
+    off, hits = nn.neighbors(q, 0.01)
+    ooff, ohits = oracle.nn_neighbors(m, pts, q, 0.01, True, mask2)
+    assert (off == ooff).all() and (hits == ohits).all()
+
+
+def test_ties_duplicates_and_degenerate_sets():
+    m = MetricSpec.euclidean(2)
+    # lattice with duplicates: ties everywhere; lowest insertion index must win
+    g = np.stack(np.meshgrid(np.arange(40) / 40.0, np.arange(40) / 40.0), -1).reshape(-1, 2)
+    pts = np.concatenate([g, g[::3]])
+    q = np.concatenate([g[::7] + 0.0125, g[::5]])
+    oi, od, oc = oracle.nn_knearest(m, pts, q, 6)
+    for grid in (True, False):
+        idx, dist, cnt = _nn(m, pts, grid).knearest(q, 6)
+        assert (idx == oi).all() and (dist == od).all(), grid
+    # all points identical (zero extent): index has no usable axis -> brute-force kernels
+    same = np.full((3000, 2), 0.25)
+    nn = _nn(m, same, grid=True)
+    idx, dist = nn.nearest(np.array([[0.3, 0.3]] * 70))
+    assert (idx == 0).all()
+    # empty set, k > n, single point
+    nn = _nn(m)
+    idx, dist = nn.nearest(np.zeros((3, 2)))
+    assert (idx == -1).all() and np.isinf(dist).all()
+    i1, d1 = nn.nearest_one([0.1, 0.2])
+    assert i1 == -1
+    nn.add(np.array([[0.5, 0.5], [0.25, 0.5]]))
+    idx, dist, cnt = nn.knearest(np.array([[0.0, 0.5]]), 5)
+    assert cnt.tolist() == [2] and idx[0].tolist() == [1, 0, -1, -1, -1]
+    off, hits = nn.neighbors(np.zeros((0, 2)), 1.0)
+    assert off.tolist() == [0] and len(hits) == 0
+
+
+def test_radius_large_hit_counts_sorted():
+    rng = np.random.default_rng(11)
+    m = MetricSpec.euclidean(3)
+    pts = rng.random((40000, 3))
+    q = rng.random((128, 3))
+    nn = _nn(m, pts, grid=True)
+    off, hits = nn.neighbors(q, 0.2)
+    ooff, ohits = oracle.nn_neighbors(m, pts, q, 0.2, True)
+    assert (off == ooff).all() and (hits == ohits).all()
+
+
+def test_edge_check_obstacle_grid_matches_oracle():
+    rng = np.random.default_rng(8)
+    c = rng.random((9996, 2))
+    hs = 0.001 + rng.random((9996, 2)) * 0.003
+    boxes = np.concatenate([c - hs, c + hs], axis=1)
+    kink = np.array([[0.3, 0, 0.51, 0.19], [0.51, 0, 0.7, 0.29], [0.3, 0.21, 0.49, 0.7], [0.49, 0.31, 0.7, 0.7]])
+    circles = np.concatenate([rng.random((300, 2)), 0.002 + rng.random((300, 1)) * 0.01], axis=1)
+    sp = SpaceSpec([0, 0], [1, 1], boxes=np.concatenate([kink, boxes]), circles=circles)
+    from pyoptimalmotionplanning_b200.backend import CudaSpace
+    s = CudaSpace(sp, 0)
+    x = rng.random((20000, 2)) * 1.1 - 0.05
+    x[:50] = boxes[:50, :2]          # exactly on obstacle corners
+    x[50:60, 0] = np.nan
+    assert (s.feasible(x) == oracle.feasible(sp, x)).all()
+    a = rng.random((20000, 2))
+    d = rng.random((20000, 2)) - 0.5
+    b = np.clip(a + d * (0.15 / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-9)) * rng.random((20000, 1)), 0, 1)
+    for res in (0.01, 0.001):
+        assert (s.edge_check(a, b, res) == oracle.edge_check(sp, a, b, res)).all()
+    # indexed form over a node table
+    ij = rng.integers(0, 20000, (30000, 2)).astype(np.int32)
+    import torch
+    nodes = torch.from_numpy(a).cuda()
+    tij = torch.from_numpy(ij).cuda()
+    ok = torch.empty(len(ij), dtype=torch.uint8, device="cuda")
+    s.edge_check_indexed_device(nodes.data_ptr(), tij.data_ptr(), len(ij), 0.01, ok.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (ok.cpu().numpy().astype(bool) == oracle.edge_check_indexed(sp, a, ij, 0.01)).all()
+
+
+def test_higher_dim_space_and_path_edges():
+    rng = np.random.default_rng(9)
+    from pyoptimalmotionplanning_b200.backend import CudaSpace
+    sp = SpaceSpec([0, 0, -np.inf, -1], [1, 1, np.inf, 1], boxes=[[0.3, 0.3, 0.7, 0.7]], obstacle_dims=(0, 1))
+    s = CudaSpace(sp, 0)
+    a = rng.random((3000, 4)) * [1, 1, 6, 2] - [0, 0, 0, 1]
+    b = rng.random((3000, 4)) * [1, 1, 6, 2] - [0, 0, 0, 1]
+    assert (s.edge_check(a, b, 0.01) == oracle.edge_check(sp, a, b, 0.01)).all()
+    g = MetricSpec.geodesic_product([("R", 2), ("SO2",), ("R", 1)], [1.0, 0.3, 2.0])
+    lens = rng.integers(1, 9, 400)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    wp = rng.random((off[-1], 4)) * [1, 1, 12, 2] - [0, 0, 3, 1]
+    assert (s.edge_check_path(g, wp, off, 0.01) == oracle.edge_check_path(sp, g, wp, off, 0.01)).all()
+
+
+def test_select_control_batched_matches_oracle():
+    from pyoptimalmotionplanning_b200.backend import CudaDynamics
+    rng = np.random.default_rng(12)
+    cases = [
+        (DynamicsSpec(_abi.DYN_DUBINS, 3, 2, _abi.COST_ABS_U0),
+         MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi]).with_cost(1.0, 2.0), 64),
+        (DynamicsSpec(_abi.DYN_PENDULUM, 2, 2, _abi.COST_TIME, dt=0.01, p=[9.8, 1, 1]),
+         MetricSpec.geodesic_product([("SO2",), ("R", 1)], [1.0, 1.0]).with_cost(1.0, None), 64),
+        (DynamicsSpec(_abi.DYN_CV, 4, 3, _abi.COST_TIME, dt=0.05), MetricSpec.euclidean(4).with_cost(0.0, None), 33),
+    ]
+    for dyn, m, S in cases:
+        B = 300
+        X = dyn.state_dim()
+        x = rng.random((B, X))
+        xd = rng.random((B, X)) * 1.5
+        u = rng.random((B, S, dyn.u_dim)) - 0.5
+        u[..., 0] = np.abs(u[..., 0]) * 0.6
+        valid = rng.random((B, S)) > 0.1
+        valid[5] = False
+        best, xb, db = CudaDynamics(dyn).select_control(m, x, xd, u, valid)
+        ob, oxb, odb = oracle.select_control(dyn, m, x, xd, u, valid)
+        # trig / pow differences can only flip candidates whose distances agree to ~1e-12
+        flips = np.nonzero(best != ob)[0]
+        for f in flips:
+            assert abs(db[f] - odb[f]) <= 1e-11 * max(1.0, abs(odb[f]))
+        assert len(flips) <= 2
+        same = best == ob
+        np.testing.assert_allclose(xb[same], oxb[same], rtol=1e-5, atol=1e-12, equal_nan=True)
+        assert best[5] == -1
+
+
+def test_fused_extend_matches_oracle():
+    from pyoptimalmotionplanning_b200.backend import CudaNN, CudaSpace, rrt_extend
+    rng = np.random.default_rng(13)
+    m = MetricSpec.euclidean(2)
+    sp = SpaceSpec([0, 0], [1, 1], boxes=[[0.3, 0.3, 0.7, 0.7], [0.1, 0.6, 0.2, 0.9]])
+    s = CudaSpace(sp, 0)
+    for n in (1, 37, 5000, 70000):
+        pts = rng.random((n, 2))
+        nn = CudaNN(m, 0)
+        nn.add(pts)
+        cur = pts
+        for t in range(40):
+            xr = rng.random(2)
+            parent, xnew, elen, added = rrt_extend(nn, s, xr, 0.15, 0.01, True)
+            if not oracle.feasible(sp, [xr])[0]:
+                assert parent == -2 and not added
+                continue
+            op, oxn, oadd = oracle.rrt_extend(m, cur, sp, xr, 0.15, 0.01)
+            assert parent == op and added == oadd and (np.array(xnew) == oxn).all()
+            assert elen == float(np.sqrt(((cur[op] - oxn) ** 2)[0] + ((cur[op] - oxn) ** 2)[1]))
+            if added:
+                cur = np.concatenate([cur, oxn[None]])
+        assert nn.size() == len(cur)
+        idx, _ = nn.nearest(rng.random((50, 2)))   # appended nodes are visible to later queries
+        assert idx.max() < len(cur)
+
+
+def test_errors_are_loud():
+    from pyoptimalmotionplanning_b200 import PompError
+    from pyoptimalmotionplanning_b200.backend import CudaNN
+    nn = CudaNN(MetricSpec.euclidean(2), 0)
+    nn.add(np.zeros((4, 2)))
+    with pytest.raises(PompError):
+        nn.knearest(np.zeros((1, 2)), 129)
+    with pytest.raises(PompError):
+        nn.remove(10)
+    with pytest.raises(PompError):
+        nn.set_mask(np.zeros(3, np.uint8))
