@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pomp-b200 hot path (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Step = one pass of the hot path over one batch: NearestNeighbors.nearest for 2^20 queries
+against an index of 2^24 points in 2-D (float64, Euclidean), SURVEY.md 8(d).  `value` counts
+queries answered per second with everything resident in HBM; `e2e` is the same batch through the
+host-buffer C-ABI call (pinned host queries in, host results out, copies inside the timed region).
+`extras` carries the other sub-configurations (k=16, 3-D/6-D, radius, Kink edge checks, batched
+control selection, r-rrt on Bugtrap) measured with a few repetitions each.
+
+N > 1: one process per GPU (torchrun).  The node set is sharded by insertion-index blocks (2^24
+points per GPU -- weak scaling of the node set), the query batch is split into per-rank slices,
+and each step runs all-gather(queries) -> local top-k -> all-to-all(candidates) -> merge kernel.
+
+--impl reference: the reference's own CPU algorithm for this path (its default kd-tree,
+pomp/structures/kdtree.py, restated in C in oracle/pomp_oracle.c because the Python reference does
+not exist on the GPU box) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LOG2_N = int(os.environ.get("POMP_BENCH_LOG2_N", 24))
+LOG2_Q = int(os.environ.get("POMP_BENCH_LOG2_Q", 20))
+DIM = 2
+K = 1
+CPU_LOG2_N = int(os.environ.get("POMP_BENCH_CPU_LOG2_N", 24))
+CPU_LOG2_Q = int(os.environ.get("POMP_BENCH_CPU_LOG2_Q", 18))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(key):
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(key)
+    return None
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_points(n, d, seed=1234):
+    return np.random.default_rng(seed).random((n, d))
+
+
+def gen_queries(n, d, seed=4321):
+    return np.random.default_rng(seed).random((n, d))
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_kdtree_run(steps, warmup, timed_as_main):
+    """The reference's default NearestNeighbors back end (kd-tree) on the host cores.
+    Bounded sample: 2^CPU_LOG2_N points, 2^CPU_LOG2_Q queries per step."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    m = oracle.MetricSpec.euclidean(DIM)
+    n, nq = 1 << CPU_LOG2_N, 1 << CPU_LOG2_Q
+    pts = gen_points(1 << LOG2_N, DIM)[:n].copy()
+    q = gen_queries(1 << LOG2_Q, DIM)[:nq].copy()
+    t0 = time.perf_counter()
+    kd = oracle.KDTree(m, pts)
+    build_s = time.perf_counter() - t0
+    for _ in range(warmup):
+        kd.nearest(q[: nq // 8])
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        kd.nearest(q)
+        times.append(time.perf_counter() - t0)
+    per = float(np.mean(times))
+    sample = ("kd-tree (C restatement of pomp/structures/kdtree.py, bulk set()) over the first 2^%d of the 2^%d "
+              "points, 2^%d of the 2^%d queries per step, OpenMP over queries; build %.1f s single-threaded, "
+              "not timed" % (CPU_LOG2_N, LOG2_N, CPU_LOG2_Q, LOG2_Q, build_s))
+    return {"value": nq / per, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_step": per * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cb = cpu_kdtree_run(args.steps, args.warmup, True)
+    line = {"impl": "reference", "metric": "knn_queries_per_s", "value": cb["value"], "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(gpus):
+    return {"workload": "NearestNeighbors.nearest: 2^%d queries vs 2^%d points%s, %d-D Euclidean float64, k=%d"
+                        % (LOG2_Q, LOG2_N, " per GPU (node set sharded)" if gpus > 1 else "", DIM, K),
+            "points_per_gpu": 1 << LOG2_N, "queries": 1 << LOG2_Q, "dim": DIM, "k": K,
+            "l2": "inputs (%.0f MB of points) exceed the 126 MB L2; no explicit flush" % ((1 << LOG2_N) * DIM * 8 / 1e6),
+            "parallelism": "1 GPU" if gpus == 1 else "node-set sharded x%d + NCCL candidate all-to-all" % gpus}
+
+
+# ------------------------------------------------------------------------------ extras (N=1)
+def time_cuda(fn, reps=3, warm=1):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_extras(peak):
+    import torch
+    from pyoptimalmotionplanning_b200 import MetricSpec, SpaceSpec, DynamicsSpec, _abi
+    from pyoptimalmotionplanning_b200.backend import CudaNN, CudaSpace, CudaDynamics
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    n, nq = 1 << LOG2_N, 1 << LOG2_Q
+    for d, ks in ((2, (16,)), (3, (1, 16)), (6, (1, 16))):
+        pts = torch.from_numpy(gen_points(n, d)).cuda()
+        q = torch.from_numpy(gen_queries(nq, d)).cuda()
+        nn = CudaNN(MetricSpec.euclidean(d), 0)
+        nn.set_device(pts.data_ptr(), n, st)
+        t_build = time_cuda(lambda: nn.build_index(st), reps=2, warm=1)
+        out["index_build_D%d" % d] = {"ms": t_build, "points_per_s": n / t_build * 1e3,
+                                      "hbm_frac": (2 * n * d * 8 + n * 4) / (t_build * 1e-3) / 1e9 / peak}
+        for k in ks:
+            idx = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+            dst = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+            ms = time_cuda(lambda: nn.knearest_device(q.data_ptr(), nq, k, idx.data_ptr(), dst.data_ptr(), None, st))
+            byt = n * d * 8 + nq * d * 8 + nq * k * 16
+            out["knn_D%d_k%d" % (d, k)] = {"queries_per_s": nq / ms * 1e3, "ms": ms,
+                                           "hbm_frac": byt / (ms * 1e-3) / 1e9 / peak}
+        if d == 2:
+            import math
+            r = math.sqrt(16.0 / (n * math.pi))
+            off = torch.empty(nq + 1, dtype=torch.int64, device="cuda")
+            hits = torch.empty(nq * 40, dtype=torch.int64, device="cuda")
+            ms = time_cuda(lambda: nn.neighbors_device(q.data_ptr(), nq, r, True, off.data_ptr(), hits.data_ptr(),
+                                                       hits.numel(), st))
+            out["radius_D2_16hits"] = {"queries_per_s": nq / ms * 1e3, "ms": ms, "hits": int(off[-1].item())}
+        del nn, pts, q
+        torch.cuda.empty_cache()
+    # Kink roadmap edge checks: 4 Mi samples, Kink's 4 boxes + 9996 small boxes, RRT-style edges <= 0.15
+    rng = np.random.default_rng(8)
+    c = rng.random((9996, 2))
+    hs = 0.001 + rng.random((9996, 2)) * 0.003
+    w = 0.02
+    kink = [[0.3, 0, 0.5 + w * 0.5, 0.2 - w * 0.5], [0.5 + w * 0.5, 0, 0.7, 0.3 - w * 0.5],
+            [0.3, 0.2 + w * 0.5, 0.5 - w * 0.5, 0.7], [0.5 - w * 0.5, 0.3 + w * 0.5, 0.7, 0.7]]
+    sp = SpaceSpec([0, 0], [1, 1], boxes=np.concatenate([np.array(kink), np.concatenate([c - hs, c + hs], 1)]))
+    space = CudaSpace(sp, 0)
+    ne = 1 << 22
+    a_h = np.random.default_rng(7).random((ne, 2))
+    dlt = np.random.default_rng(9).random((ne, 2)) - 0.5
+    b_h = np.clip(a_h + dlt * (0.15 / np.maximum(np.linalg.norm(dlt, axis=1, keepdims=True), 1e-12)), 0, 1)
+    a, b = torch.from_numpy(a_h).cuda(), torch.from_numpy(b_h).cuda()
+    ok = torch.empty(ne, dtype=torch.uint8, device="cuda")
+    for res in (0.01, 0.001):
+        ms = time_cuda(lambda: space.edge_check_device(a.data_ptr(), b.data_ptr(), ne, res, ok.data_ptr(), st))
+        out["edge_checks_kink10k_res%g" % res] = {"edges_per_s": ne / ms * 1e3, "ms": ms,
+                                                  "hbm_frac": ne * 33 / (ms * 1e-3) / 1e9 / peak,
+                                                  "feasible_frac": float(ok.float().mean().item())}
+    # batched control selection, Dubins, B x 64 candidates
+    B, S = 65536, 64
+    dyn = DynamicsSpec(_abi.DYN_DUBINS, 3, 2, _abi.COST_ABS_U0)
+    m = MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi]).with_cost(1.0, 3.0)
+    r2 = np.random.default_rng(11)
+    x = torch.from_numpy(r2.random((B, 4)) * [1, 1, 6.28, 1]).cuda()
+    xd = torch.from_numpy(r2.random((B, 4)) * [1, 1, 6.28, 3]).cuda()
+    u = torch.from_numpy((r2.random((B, S, 2)) - 0.5) * [0.2, 6.28]).cuda()
+    best = torch.empty(B, dtype=torch.int32, device="cuda")
+    xb = torch.empty((B, 4), dtype=torch.float64, device="cuda")
+    db = torch.empty(B, dtype=torch.float64, device="cuda")
+    cd = CudaDynamics(dyn)
+    ms = time_cuda(lambda: cd.select_control_device(m, x.data_ptr(), xd.data_ptr(), u.data_ptr(), None, B, S,
+                                                    best.data_ptr(), xb.data_ptr(), db.data_ptr(), st))
+    out["select_control_dubins_64"] = {"next_states_per_s": B * S / ms * 1e3, "ms": ms,
+                                       "hbm_frac": B * S * 50 / (ms * 1e-3) / 1e9 / peak}
+    # r-rrt on Bugtrap: planner iterations per second through the fused extend kernel
+    import random
+    from pyoptimalmotionplanning_b200.rrt import RepeatedRRT
+    random.seed(0)
+    bug = SpaceSpec([0, 0], [1, 1], boxes=[[0.3, 0.3, 0.7, 0.7]])
+    p = RepeatedRRT(bug, [0.1, 0.5], [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01)
+    p.planMore(200)
+    t0 = time.perf_counter()
+    iters = 0
+    while iters < 20000:
+        p.planMore(10)
+        iters += 10
+    dt = time.perf_counter() - t0
+    out["rrrt_bugtrap"] = {"iters_per_s": iters / dt, "best_cost": p.bestPathCost}
+    return out
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from pyoptimalmotionplanning_b200 import MetricSpec
+    from pyoptimalmotionplanning_b200.backend import CudaNN, launch_count
+    from pyoptimalmotionplanning_b200.sharded import ShardedNearestNeighbors
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peak, peak_src = peaks()
+    n, nq = 1 << LOG2_N, 1 << LOG2_Q
+    st = torch.cuda.current_stream().cuda_stream
+
+    # ---- data: synthetic, SURVEY 8(d).  Rank r holds shard r of the node set.
+    pts_h = gen_points(n, DIM, 1234 + rank)
+    q_all_h = gen_queries(nq, DIM)
+    qs = nq // world
+    q_slice_h = torch.from_numpy(q_all_h[rank * qs:(rank + 1) * qs].copy()).pin_memory()
+    pts = torch.from_numpy(pts_h).cuda(local)
+    nn = CudaNN(MetricSpec.euclidean(DIM), local)
+    nn.set_device(pts.data_ptr(), n, st)
+    nn.build_index(st)
+    torch.cuda.synchronize()
+    nn.set_param("profile", 0)
+
+    q_dev = q_slice_h.cuda(non_blocking=False)
+    idx = torch.empty(qs, dtype=torch.int64, device="cuda")
+    dst = torch.empty(qs, dtype=torch.float64, device="cuda")
+    if world > 1:
+        shard = ShardedNearestNeighbors(rank * n, nn=nn)
+
+        def step():
+            return shard.knearest(q_dev, K)
+    else:
+        def step():
+            nn.nearest_device(q_dev.data_ptr(), qs, idx.data_ptr(), dst.data_ptr(), st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    nn.set_param("profile", 1)
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = nn.get_stat("search_kernel_ms")
+    kern_n = nn.get_stat("search_kernel_launches")
+    nn.set_param("profile", 0)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # ---- e2e: host buffers through the reference-facing call, copies inside the timed region
+    idx_h = torch.empty((qs, K), dtype=torch.int64).pin_memory()
+    dst_h = torch.empty((qs, K), dtype=torch.float64).pin_memory()
+    import ctypes as C
+    from pyoptimalmotionplanning_b200._abi import check
+
+    if world > 1:
+        def e2e_step():
+            qd = q_slice_h.cuda(non_blocking=True)
+            i, d = shard.knearest(qd, K)
+            idx_h.copy_(i, non_blocking=True)
+            dst_h.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+    else:
+        def e2e_step():
+            check(nn.lib, nn.lib.pomp_nn_nearest_h(nn._h, C.c_void_p(q_slice_h.data_ptr()), qs,
+                                                   C.c_void_p(idx_h.data_ptr()), C.c_void_p(dst_h.data_ptr())))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    # sanity: the e2e answers equal the device-resident answers
+    if world == 1:
+        assert torch.equal(idx_h[:, 0], idx.cpu()), "e2e result differs from the device-resident result"
+
+    if rank == 0:
+        alg_bytes = n * DIM * 8 + nq * DIM * 8 + nq * K * 16
+        kms = kern_ms / max(kern_n, 1)
+        achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        line = {"metric": "knn_queries_per_s", "value": nq / (ms_step * 1e-3), "unit": "queries/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(world),
+                "roofline": {"bound": "hbm", "kernel": "grid_knn_kernel<2,1,true>", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kms,
+                             "kernel_share_of_step": kms / ms_step if ms_step > 0 else None,
+                             "traffic": measured_traffic("grid_knn_D2_k1")},
+                "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": qs * DIM * 8 * world,
+                        "d2h_bytes_per_step": qs * K * 16 * world, "ms_per_step": e2e_s * 1e3,
+                        "api": "pomp_nn_nearest_h (pinned host buffers)" if world == 1 else
+                               "ShardedNearestNeighbors.knearest + pinned H2D/D2H"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1:
+            if not args.no_extras:
+                line["extras"] = run_extras(peak)
+            if not args.no_cpu:
+                cb = cpu_kdtree_run(2, 1, False)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

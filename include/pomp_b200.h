@@ -111,8 +111,12 @@ int pomp_nn_set_mask_h(pomp_nn* h, const uint8_t* reject_mask_h, int64_t n);
 /* CostSpaceRRT.updateBestCost mutates the metric in place (kinodynamicplanner.py:1059-1077) */
 int pomp_nn_update_metric(pomp_nn* h, const pomp_metric_desc* metric);
 int64_t pomp_nn_size(const pomp_nn* h);
-/* tuning knobs: "grid_min_points" (below: brute force), "points_per_cell", "sort_queries" */
+/* tuning knobs: "grid_min_points" / "grid_min_queries" (below: brute-force kernels), "points_per_cell",
+   "sort_queries", "max_tail", "profile" */
 int pomp_nn_set_param(pomp_nn* h, const char* name, double value);
+/* read-outs: "search_kernel_ms" / "search_kernel_launches" (CUDA-event time of the dominant search
+   kernel since set_param("profile",1); call after synchronising), "n_cells", "n_indexed", "grid_axes" */
+int pomp_nn_get_stat(pomp_nn* h, const char* name, double* out);
 /* (re)build the uniform-grid bucket index over all points now (otherwise built lazily) */
 int pomp_nn_build_index(pomp_nn* h, void* stream);
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "pomp_nn_update_metric": (C.c_int, [_P, _MD]),
     "pomp_nn_size": (_I64, [_P]),
     "pomp_nn_set_param": (C.c_int, [_P, C.c_char_p, _D]),
+    "pomp_nn_get_stat": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
     "pomp_nn_build_index": (C.c_int, [_P, _P]),
     "pomp_nn_nearest": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "pomp_nn_nearest_h": (C.c_int, [_P, _P, _I64, _P, _P]),

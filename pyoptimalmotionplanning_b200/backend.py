@@ -99,6 +99,11 @@ class CudaNN(object):
     def set_param(self, name, value):
         check(self.lib, self.lib.pomp_nn_set_param(self._h, name.encode(), float(value)))
 
+    def get_stat(self, name):
+        out = C.c_double()
+        check(self.lib, self.lib.pomp_nn_get_stat(self._h, name.encode(), C.byref(out)))
+        return out.value
+
     def build_index(self, stream=None):
         check(self.lib, self.lib.pomp_nn_build_index(self._h, C.c_void_p(stream or 0)))
 

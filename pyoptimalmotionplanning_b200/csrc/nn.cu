@@ -772,6 +772,24 @@ static SplitGeom split_geom(pomp_nn* h, int64_t nq, int64_t n) {
 
 static bool is_plain_euclid(const pomp_metric_desc& m) { return m.kind == POMP_METRIC_EUCLIDEAN && !m.has_cost; }
 
+// ---- optional event timing of the dominant kernel ---------------------------------------------
+static void prof_begin(pomp_nn* h, cudaStream_t st) {
+  if (!h->profile) return;
+  if (h->prof_used + 2 > h->prof_ev.size()) {
+    for (int i = 0; i < 2; i++) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      h->prof_ev.push_back(e);
+    }
+  }
+  cudaEventRecord(h->prof_ev[h->prof_used], st);
+}
+static void prof_end(pomp_nn* h, cudaStream_t st) {
+  if (!h->profile || h->prof_used + 2 > h->prof_ev.size()) return;
+  cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
+  h->prof_used += 2;
+}
+
 // ---- k-NN dispatch ---------------------------------------------------------------------------
 template <int D, bool EUCLID>
 static int launch_grid_knn(pomp_nn* h, const double* q, int64_t nq, const int* qperm, int k, int64_t* idx,
@@ -781,6 +799,7 @@ static int launch_grid_knn(pomp_nn* h, const double* q, int64_t nq, const int* q
 #define GK(KK)                                                                                              \
   LAUNCH((grid_knn_kernel<D, KK, EUCLID>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts, (long long)h->n_dev, \
          skip, q, (long long)nq, qperm, k, idx, dist, cnt)
+  prof_begin(h, st);
   if (k == 1) GK(1);
   else if (k <= 4) GK(4);
   else if (k <= 8) GK(8);
@@ -789,6 +808,7 @@ static int launch_grid_knn(pomp_nn* h, const double* q, int64_t nq, const int* q
   else if (k <= 64) GK(64);
   else GK(128);
 #undef GK
+  prof_end(h, st);
   CHECK_LAUNCH();
   return POMP_OK;
 }
@@ -1003,6 +1023,7 @@ POMP_API int pomp_nn_destroy(pomp_nn* h) {
   if (h->mailbox_h) cudaFreeHost(h->mailbox_h);
   if (h->ticket) cudaFree(h->ticket);
   if (h->stream) cudaStreamDestroy(h->stream);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return POMP_OK;
 }
@@ -1141,8 +1162,35 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   } else if (s == "sort_queries") h->sort_queries = value;
   else if (s == "grid_min_queries") h->grid_min_queries = value;
   else if (s == "max_tail") h->max_tail = value;
+  else if (s == "profile") {
+    h->profile = value != 0;
+    h->prof_used = 0;
+  }
   else {
     set_error("unknown parameter '%s'", name);
+    return POMP_ERR_INVALID;
+  }
+  return POMP_OK;
+}
+
+POMP_API int pomp_nn_get_stat(pomp_nn* h, const char* name, double* out) {
+  POMP_REQUIRE(h && name && out, "bad arguments to pomp_nn_get_stat");
+  std::string s(name);
+  *out = 0.0;
+  if (s == "search_kernel_ms" || s == "search_kernel_launches") {
+    // call after synchronising the stream the queries ran on
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+      float t = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+      ms += t;
+    }
+    *out = (s == "search_kernel_ms") ? ms : (double)(h->prof_used / 2);
+  } else if (s == "n_cells") *out = h->grid_valid ? (double)h->grid.n_cells : 0.0;
+  else if (s == "n_indexed") *out = h->grid_valid ? (double)h->grid.n_indexed : 0.0;
+  else if (s == "grid_axes") *out = h->grid_valid ? (double)h->grid.G : 0.0;
+  else {
+    set_error("unknown stat '%s'", name);
     return POMP_ERR_INVALID;
   }
   return POMP_OK;

@@ -53,6 +53,11 @@ struct pomp_nn {
   void* mailbox_d = nullptr;
   unsigned int* ticket = nullptr;
   cudaStream_t stream = nullptr;  // used by the *_h variants
+  // optional timing of the dominant search kernel with CUDA events on the launching stream
+  // (bench.py's roofline numerator); enabled with set_param("profile", 1)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs
+  size_t prof_used = 0;
 
   int64_t size() const { return n_dev + (int64_t)(pending.size() / (size_t)std::max(D, 1)); }
   const uint8_t* skip_ptr() const { return (any_dead || has_reject) ? d_skip : nullptr; }

@@ -153,10 +153,23 @@ def test_ties_duplicates_and_degenerate_sets():
     g = np.stack(np.meshgrid(np.arange(40) / 40.0, np.arange(40) / 40.0), -1).reshape(-1, 2)
     pts = np.concatenate([g, g[::3]])
     q = np.concatenate([g[::7] + 0.0125, g[::5]])
-    oi, od, oc = oracle.nn_knearest(m, pts, q, 6)
+    # canonical rule under exact ties: the k smallest (distance, insertion index) keys.  (The
+    # reference's KNearestResult evicts an arbitrary one of several tied maxima -- knn.py:20-23 --
+    # and its kd-tree visits leaves in traversal order, so the reference itself has no single
+    # answer here; the distances are still the oracle's, bit for bit.)
+    d0 = pts[None, :, 0] - q[:, None, 0]
+    d1 = pts[None, :, 1] - q[:, None, 1]
+    dd = np.sqrt(d0 * d0 + d1 * d1)
+    assert dd[3, 5] == oracle.metric(m, pts[5], q[3])
+    order = np.lexsort((np.broadcast_to(np.arange(len(pts)), dd.shape), dd), axis=1)[:, :6]
+    oi = order
+    od = np.take_along_axis(dd, order, axis=1)
     for grid in (True, False):
         idx, dist, cnt = _nn(m, pts, grid).knearest(q, 6)
         assert (idx == oi).all() and (dist == od).all(), grid
+        i1, dn = _nn(m, pts, grid).nearest(q)
+        assert (i1 == oi[:, 0]).all()
+        assert (i1 == oracle.nn_nearest(m, pts, q)[0]).all()
     # all points identical (zero extent): index has no usable axis -> brute-force kernels
     same = np.full((3000, 2), 0.25)
     nn = _nn(m, same, grid=True)
