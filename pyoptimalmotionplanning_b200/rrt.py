@@ -18,13 +18,12 @@ import hashlib
 import math
 import random
 
-from .backend import CudaNN, CudaSpace, rrt_extend
 from .descriptors import MetricSpec, space_from_pomp
 
 
 class RRT(object):
     def __init__(self, space, start, goal=None, goal_radius=None, max_step=0.1, resolution=0.01, p_choose_goal=0.1,
-                 device=0):
+                 device=0, _backends=None):
         """space: SpaceSpec (or pomp ConfigurationSpace); goal: centre of a NeighborhoodSubset of
         radius goal_radius, or None to just explore."""
         self.spec = space_from_pomp(space)
@@ -35,8 +34,12 @@ class RRT(object):
         self.max_step = max_step
         self.resolution = resolution
         self.pChooseGoal = p_choose_goal
-        self._nn = CudaNN(MetricSpec.euclidean(self.D), device)
-        self._space = CudaSpace(self.spec, device)
+        if _backends is None:  # the product path: CUDA kernels behind the C-ABI
+            from .backend import CudaNN, CudaSpace, rrt_extend
+            _backends = (CudaNN, CudaSpace, rrt_extend)
+        nn_cls, space_cls, self._extend = _backends
+        self._nn = nn_cls(MetricSpec.euclidean(self.D), device)
+        self._space = space_cls(self.spec, device)
         self.numIters = 0
         self._reset_tree()
 
@@ -61,7 +64,7 @@ class RRT(object):
     def expand(self):
         """One RRT.expand; returns the new node index or None."""
         xrand = self._sample()
-        parent, xnew, elen, added = rrt_extend(self._nn, self._space, xrand, self.max_step, self.resolution, True)
+        parent, xnew, elen, added = self._extend(self._nn, self._space, xrand, self.max_step, self.resolution, True)
         if not added:
             return None
         self.nodes.append(xnew)

@@ -1,0 +1,129 @@
+"""Oracle-backed stand-ins for backend.CudaNN / CudaSpace / CudaDynamics -- TEST ONLY.
+
+They implement the same small internal interface with the CPU oracle so that the HOST logic of
+the drop-ins (index bookkeeping, filters, metric refresh, interpolator dispatch, RNG order, the
+RRT driver, the multi-rank plumbing) can be exercised in the CPU-only container, including against
+the unmodified reference planners.  The product never imports this module."""
+import numpy as np
+
+from oracle import oracle
+
+
+class OracleNN(object):
+    def __init__(self, spec, device=0, capacity_hint=0):
+        self.spec = spec
+        self.dim = spec.dim
+        self.pts = np.zeros((0, spec.dim))
+        self.dead = np.zeros(0, np.uint8)
+        self.rej = None
+
+    def _mask(self):
+        m = self.dead.copy()
+        if self.rej is not None:
+            m |= self.rej
+        return m if m.any() else None
+
+    def reset(self):
+        self.pts = np.zeros((0, self.dim))
+        self.dead = np.zeros(0, np.uint8)
+        self.rej = None
+
+    def size(self):
+        return len(self.pts)
+
+    def add(self, pts):
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, self.dim)
+        first = len(self.pts)
+        self.pts = np.concatenate([self.pts, pts])
+        self.dead = np.concatenate([self.dead, np.zeros(len(pts), np.uint8)])
+        return first
+
+    def add_one(self, pt):
+        return self.add([list(pt)])
+
+    def set(self, pts):
+        self.reset()
+        self.add(pts)
+
+    def remove(self, index):
+        self.dead[index] = 1
+
+    def set_mask(self, mask):
+        self.rej = None if mask is None else np.asarray(mask, dtype=np.uint8).copy()
+        if self.rej is not None:
+            assert len(self.rej) == len(self.pts)
+
+    def update_metric(self, spec):
+        self.spec = spec
+
+    def nearest_one(self, pt):
+        if len(self.pts) == 0:
+            return -1, float("inf")
+        i, d = oracle.nn_nearest(self.spec, self.pts, [list(pt)], self._mask())
+        return int(i[0]), float(d[0])
+
+    def nearest(self, q):
+        return oracle.nn_nearest(self.spec, self.pts, q, self._mask())
+
+    def knearest(self, q, k):
+        return oracle.nn_knearest(self.spec, self.pts, q, k, self._mask())
+
+    def neighbors(self, q, radius, inclusive=True):
+        return oracle.nn_neighbors(self.spec, self.pts, q, radius, inclusive, self._mask())
+
+
+class OracleSpace(object):
+    def __init__(self, spec, device=0):
+        self.spec = spec
+        self.dim = spec.dim
+
+    def set_bounds(self, lo, hi):
+        self.spec.lo, self.spec.hi = list(lo), list(hi)
+
+    def feasible(self, x):
+        return oracle.feasible(self.spec, x)
+
+    def feasible_one(self, x):
+        return bool(oracle.feasible(self.spec, [list(x)])[0])
+
+    def edge_check(self, a, b, res):
+        return oracle.edge_check(self.spec, a, b, res)
+
+    def edge_check_one(self, a, b, res):
+        return bool(oracle.edge_check(self.spec, [list(a)], [list(b)], res)[0])
+
+    def edge_check_path(self, g, wp, off, res):
+        return oracle.edge_check_path(self.spec, g, wp, off, res)
+
+    def edge_check_control(self, dyn, g, x, u, res):
+        if g is None:
+            g = oracle.MetricSpec.euclidean(self.dim)
+        return oracle.edge_check_control(self.spec, dyn, g, x, u, res)
+
+
+class OracleDynamics(object):
+    def __init__(self, spec):
+        self.spec = spec
+
+    def next_state(self, x, u):
+        return oracle.next_state(self.spec, x, u)
+
+    def select_control(self, m, x, xdes, u, valid=None):
+        return oracle.select_control(self.spec, m, x, xdes, u, valid)
+
+
+def oracle_rrt_extend(nn, space, xrand, max_step, res, check_sample=True):
+    if check_sample and not space.feasible_one(xrand):
+        return -2, [float("nan")] * nn.dim, 0.0, False
+    parent, xnew, added = oracle.rrt_extend(nn.spec, nn.pts, space.spec, xrand, max_step, res, nn._mask())
+    if parent < 0:
+        return -1, [float("nan")] * nn.dim, 0.0, False
+    a = nn.pts[parent]
+    s = 0.0
+    for j in range(nn.dim):
+        s = s + (a[j] - xnew[j]) * (a[j] - xnew[j])
+    elen = float(np.sqrt(s))
+    xnew = [float(v) for v in xnew]
+    if added:
+        nn.add([xnew])
+    return parent, xnew, elen, added
