@@ -1,0 +1,266 @@
+// grid_fast.cuh -- register-resident grid search for the plain Euclidean metric with every
+// coordinate gridded (the 2-D..6-D point-cloud configurations of BASELINE.json).
+//
+// Same algorithm and the same exactness argument as grid.cuh, specialised so that nothing is
+// indexed dynamically (axes are unrolled by template recursion, the k-list lives in registers):
+//   * candidates carry their SORTED POSITION; the insertion index is fetched from sidx[] only when
+//     two distances are exactly equal (index tie-break) and once per result at the end;
+//   * pruning is done on squared quantities against tsq = fl(T*T)*(1+2^-50): s > tsq implies
+//     fl(sqrt(s)) > T, so no sqrt is spent on rows, cells or far candidates; everything that
+//     survives is compared on the rooted value exactly as the reference does (vectorops.py:101).
+#pragma once
+#include "grid.cuh"
+#include "topk.cuh"
+
+namespace pomp {
+
+struct IdxResolver {
+  const int* __restrict__ sidx;
+  int n_indexed;
+  // sorted slot -> insertion index; tail points (never sorted) use their insertion index as slot
+  __device__ __forceinline__ int operator()(int pos) const { return pos < n_indexed ? __ldg(sidx + pos) : pos; }
+};
+
+__device__ __forceinline__ double tsq_of(double T) { return (T * T) * (1.0 + 0x1p-50); }
+
+// Sorted list of the K best (distance, position); ties resolved lazily through the resolver.
+// The list always keeps K entries (a runtime k <= K is served by its first k entries: the k best
+// are a prefix of the K best).  No runtime slot arithmetic: with it, LLVM folds the unrolled
+// selects back into a dynamically indexed local array and the list leaves the register file.
+template <int K>
+struct PosTopK {
+  static_assert(K <= 32, "register-resident list: larger k goes through the generic kernel");
+  double d[K];
+  int p[K];
+  double T, tsq;  // current K-th distance and its squared prune bound
+  IdxResolver res;
+
+  __device__ __forceinline__ void init(IdxResolver r) {
+    res = r;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      d[j] = POMP_INF;
+      p[j] = -1;
+    }
+    T = POMP_INF;
+    tsq = POMP_INF;
+  }
+  __device__ __forceinline__ double threshold() const { return T; }
+  __device__ __forceinline__ double tsq_up() const { return tsq; }
+  __device__ __forceinline__ bool full() const { return T < POMP_INF; }
+  // (cd,cp) < slot j ?
+  __device__ __forceinline__ bool less_slot(double cd, int cp, int j) const {
+    if (cd < d[j]) return true;
+    if (cd == d[j] && p[j] >= 0) return res(cp) < res(p[j]);
+    return false;
+  }
+  // s = squared distance
+  __device__ __forceinline__ void offer_sq(double s, int pos) {
+    if (!(s <= tsq)) return;  // also rejects NaN
+    double cd = sqrt(s);
+    if (!(cd < POMP_INF)) return;
+    if (!less_slot(cd, pos, K - 1)) return;  // must beat the current worst kept entry
+#pragma unroll
+    for (int j = K - 1; j >= 1; j--) {
+      bool lt_prev = less_slot(cd, pos, j - 1);
+      if (lt_prev) {
+        d[j] = d[j - 1];
+        p[j] = p[j - 1];
+      } else if (less_slot(cd, pos, j)) {
+        d[j] = cd;
+        p[j] = pos;
+      }
+    }
+    if (less_slot(cd, pos, 0)) {
+      d[0] = cd;
+      p[0] = pos;
+    }
+    T = d[K - 1];
+    tsq = tsq_of(T);
+  }
+};
+
+// fixed-radius collector (count or fill)
+template <bool FILL>
+struct RadiusFast {
+  double radius, tsq;
+  int inclusive;
+  long long cnt;
+  IdxResolver res;
+  int64_t* out;
+  __device__ __forceinline__ double threshold() const { return radius; }
+  __device__ __forceinline__ double tsq_up() const { return tsq; }
+  __device__ __forceinline__ void offer_sq(double s, int pos) {
+    if (!(s <= tsq)) return;
+    double d = sqrt(s);
+    bool hit = inclusive ? (d <= radius) : (d < radius);
+    if (hit) {
+      if (FILL) out[cnt] = res(pos);
+      cnt++;
+    }
+  }
+};
+
+template <int D>
+__device__ __forceinline__ double sqdist(const double (&p)[D], const double (&q)[D]) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double t = p[i] - q[i];
+    s = s + t * t;
+  }
+  return s;
+}
+
+template <int D, class C>
+__device__ __forceinline__ void scan_run(const GridDev& g, const uint8_t* __restrict__ skip, const double (&q)[D],
+                                         C& c, int s, int t) {
+  for (int pos = s; pos < t; pos++) {
+    if (skip && skip[__ldg(g.sidx + pos)]) continue;
+    double p[D];
+    load_point<D>(g.spts, pos, p);
+    c.offer_sq(sqdist<D>(p, q), pos);
+  }
+}
+
+// squared lower bound with gaps on axes >= A (compile-time), summed in coordinate order
+template <int D, int A>
+__device__ __forceinline__ double gap_sq(const double (&gap)[D]) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double gi = i >= A ? gap[i] : 0.0;
+    s = s + gi * gi;
+  }
+  return s;
+}
+
+template <int D, int A>
+struct FastLevel {
+  template <class C>
+  static __device__ __forceinline__ void run(const GridDev& g, const uint8_t* __restrict__ skip,
+                                             const double (&q)[D], double (&gap)[D], long long base, C& c, int w0,
+                                             int w1) {
+    int lo, hi;
+    grid_range(g, A, q[A], c.threshold(), &lo, &hi);
+    for (int cc = lo; cc <= hi; cc++) {
+      gap[A] = grid_gap(g, A, cc, q[A]);
+      if (gap_sq<D, A>(gap) > c.tsq_up()) continue;
+      FastLevel<D, A - 1>::run(g, skip, q, gap, base + (long long)cc * g.stride[A], c, w0, w1);
+    }
+  }
+};
+
+template <int D>
+struct FastLevel<D, 0> {
+  template <class C>
+  static __device__ __forceinline__ void run(const GridDev& g, const uint8_t* __restrict__ skip,
+                                             const double (&q)[D], double (&gap)[D], long long base, C& c, int w0,
+                                             int w1) {
+    int lo, hi;
+    grid_range(g, 0, q[0], c.threshold(), &lo, &hi);
+    while (lo < hi) {
+      gap[0] = grid_gap(g, 0, lo, q[0]);
+      if (gap_sq<D, 0>(gap) > c.tsq_up()) lo++;
+      else break;
+    }
+    while (hi > lo) {
+      gap[0] = grid_gap(g, 0, hi, q[0]);
+      if (gap_sq<D, 0>(gap) > c.tsq_up()) hi--;
+      else break;
+    }
+    int s = __ldg(g.cell_start + base + lo);
+    int t = __ldg(g.cell_start + base + hi + 1);
+    // positions [w0,w1) were offered in phase A
+    if (s < w1 && t > w0) {
+      scan_run<D>(g, skip, q, c, s, min(t, w0));
+      scan_run<D>(g, skip, q, c, max(s, w1), t);
+    } else {
+      scan_run<D>(g, skip, q, c, s, t);
+    }
+  }
+};
+
+// points appended after the last index build: their "position" is their insertion index
+template <int D, class C>
+__device__ __forceinline__ void scan_tail(const GridDev& g, const double* __restrict__ pts, long long n,
+                                          const uint8_t* __restrict__ skip, const double (&q)[D], C& c) {
+  for (long long i = g.n_indexed; i < n; i++) {
+    if (skip && skip[i]) continue;
+    double p[D];
+    load_point<D>(pts, i, p);
+    c.offer_sq(sqdist<D>(p, q), (int)i);
+  }
+}
+
+template <int D, int K>
+__global__ void __launch_bounds__(128)
+grid_knn_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                     const double* __restrict__ q, long long nq, const int* __restrict__ qperm, int k,
+                     int64_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ out_cnt) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  long long qi = qperm ? (long long)__ldg(qperm + t) : t;
+  double qq[D];
+  load_point<D>(q, qi, qq);
+  PosTopK<K> top;
+  top.init(IdxResolver{g.sidx, g.n_indexed});
+  // phase A: the query's home cell (its points are close in every coordinate), widened to at
+  // least k sorted-order neighbours; grown further only while masked points leave the list short
+  long long home = 0;
+#pragma unroll
+  for (int a = 0; a < D; a++) home += (long long)grid_cell(g, a, qq[a]) * g.stride[a];
+  int hs = __ldg(g.cell_start + home), he = __ldg(g.cell_start + home + 1);
+  int center = (hs + he) >> 1;
+  int w0 = min(hs, max(0, center - K)), w1 = max(he, min(g.n_indexed, center + K));
+  scan_run<D>(g, skip, qq, top, w0, w1);
+  while (!top.full() && (w0 > 0 || w1 < g.n_indexed)) {
+    int len = max(w1 - w0, 1);
+    if (w0 > 0) {
+      int nw0 = max(0, w0 - len);
+      scan_run<D>(g, skip, qq, top, nw0, w0);
+      w0 = nw0;
+    } else {
+      int nw1 = min(g.n_indexed, w1 + len);
+      scan_run<D>(g, skip, qq, top, w1, nw1);
+      w1 = nw1;
+    }
+  }
+  double gap[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) gap[i] = 0.0;
+  FastLevel<D, D - 1>::run(g, skip, qq, gap, 0LL, top, w0, w1);
+  scan_tail<D>(g, pts, n, skip, qq, top);
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++)
+    if (j < k) {
+      bool fin = top.d[j] < POMP_INF;
+      out_idx[qi * k + j] = fin ? (int64_t)top.res(top.p[j]) : -1;
+      out_dist[qi * k + j] = top.d[j];
+      cnt += fin;
+    }
+  if (out_cnt) out_cnt[qi] = cnt;
+}
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(128)
+grid_radius_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                        const double* __restrict__ q, long long nq, double radius, int inclusive,
+                        int* __restrict__ counts, const int64_t* __restrict__ offsets, int64_t* __restrict__ out) {
+  long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  double qq[D];
+  load_point<D>(q, qi, qq);
+  RadiusFast<FILL> c{radius, tsq_of(radius), inclusive, 0, IdxResolver{g.sidx, g.n_indexed},
+                     FILL ? out + offsets[qi] : nullptr};
+  double gap[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) gap[i] = 0.0;
+  FastLevel<D, D - 1>::run(g, skip, qq, gap, 0LL, c, 0, 0);
+  scan_tail<D>(g, pts, n, skip, qq, c);
+  if (FILL) heapsort_i64(out + offsets[qi], c.cnt);
+  else counts[qi] = (int)c.cnt;
+}
+
+}  // namespace pomp

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "grid.cuh"
+#include "grid_fast.cuh"
 #include "nn_handle.cuh"
 #include "scan.cuh"
 #include "topk.cuh"
@@ -476,7 +477,7 @@ grid_knn_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts, l
   for (int a = 0; a < g.G; a++) home += (long long)grid_cell(g, a, qq[g.gdim[a]]) * g.stride[a];
   int hs = __ldg(g.cell_start + home), he = __ldg(g.cell_start + home + 1);
   int center = (hs + he) >> 1;
-  int w0 = max(0, center - k), w1 = min(g.n_indexed, center + k);
+  int w0 = max(0, center - K), w1 = min(g.n_indexed, center + K);
   {
     int a0 = w0, a1 = w1;
     while (true) {
@@ -512,7 +513,7 @@ grid_knn_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts, l
     if (top.maybe(d)) top.insert(d, (int)i);
   }
   int cnt = 0;
-#pragma unroll
+#pragma unroll(K <= 32 ? K : 1)
   for (int j = 0; j < K; j++)
     if (j < k) {
       bool fin = top.d[j] < POMP_INF;
@@ -546,39 +547,6 @@ struct RadiusColl {
     }
   }
 };
-
-__device__ __forceinline__ void heapsort_i64(int64_t* a, long long n) {
-  if (n < 2) return;
-  for (long long start = n / 2 - 1; start >= 0; start--) {
-    long long root = start;
-    while (true) {
-      long long child = 2 * root + 1;
-      if (child >= n) break;
-      if (child + 1 < n && a[child] < a[child + 1]) child++;
-      if (a[root] >= a[child]) break;
-      int64_t t = a[root];
-      a[root] = a[child];
-      a[child] = t;
-      root = child;
-    }
-  }
-  for (long long end = n - 1; end > 0; end--) {
-    int64_t t = a[0];
-    a[0] = a[end];
-    a[end] = t;
-    long long root = 0;
-    while (true) {
-      long long child = 2 * root + 1;
-      if (child >= end) break;
-      if (child + 1 < end && a[child] < a[child + 1]) child++;
-      if (a[root] >= a[child]) break;
-      int64_t t2 = a[root];
-      a[root] = a[child];
-      a[child] = t2;
-      root = child;
-    }
-  }
-}
 
 template <int D, bool EUCLID, bool FILL>
 __global__ void __launch_bounds__(128)
@@ -791,13 +759,12 @@ static void prof_end(pomp_nn* h, cudaStream_t st) {
 }
 
 // ---- k-NN dispatch ---------------------------------------------------------------------------
-template <int D, bool EUCLID>
-static int launch_grid_knn(pomp_nn* h, const double* q, int64_t nq, const int* qperm, int k, int64_t* idx,
-                           double* dist, int32_t* cnt, cudaStream_t st) {
+static int launch_grid_knn_generic(pomp_nn* h, const double* q, int64_t nq, const int* qperm, int k, int64_t* idx,
+                                   double* dist, int32_t* cnt, cudaStream_t st) {
   int blocks = (int)((nq + 127) / 128);
   const uint8_t* skip = h->skip_ptr();
 #define GK(KK)                                                                                              \
-  LAUNCH((grid_knn_kernel<D, KK, EUCLID>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts, (long long)h->n_dev, \
+  LAUNCH((grid_knn_kernel<0, KK, false>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts, (long long)h->n_dev, \
          skip, q, (long long)nq, qperm, k, idx, dist, cnt)
   prof_begin(h, st);
   if (k == 1) GK(1);
@@ -807,6 +774,27 @@ static int launch_grid_knn(pomp_nn* h, const double* q, int64_t nq, const int* q
   else if (k <= 32) GK(32);
   else if (k <= 64) GK(64);
   else GK(128);
+#undef GK
+  prof_end(h, st);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+// plain Euclidean metric, every coordinate a grid axis: register-resident kernels (grid_fast.cuh)
+template <int D>
+static int launch_grid_knn_fast(pomp_nn* h, const double* q, int64_t nq, const int* qperm, int k, int64_t* idx,
+                                double* dist, int32_t* cnt, cudaStream_t st) {
+  int blocks = (int)((nq + 127) / 128);
+  const uint8_t* skip = h->skip_ptr();
+#define GK(KK)                                                                                                 \
+  LAUNCH((grid_knn_fast_kernel<D, KK>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, \
+         (long long)nq, qperm, k, idx, dist, cnt)
+  prof_begin(h, st);
+  if (k == 1) GK(1);
+  else if (k <= 4) GK(4);
+  else if (k <= 8) GK(8);
+  else if (k <= 16) GK(16);
+  else GK(32);
 #undef GK
   prof_end(h, st);
   CHECK_LAUNCH();
@@ -833,16 +821,16 @@ static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx
     CHECK_LAUNCH();
     qperm = h->qperm.p;
   }
-  if (is_plain_euclid(h->metric)) {
+  if (is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32) {
     switch (h->D) {
-      case 2: return launch_grid_knn<2, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
-      case 3: return launch_grid_knn<3, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
-      case 4: return launch_grid_knn<4, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
-      case 6: return launch_grid_knn<6, true>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 2: return launch_grid_knn_fast<2>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 3: return launch_grid_knn_fast<3>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 4: return launch_grid_knn_fast<4>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 6: return launch_grid_knn_fast<6>(h, q, nq, qperm, k, idx, dist, cnt, st);
       default: break;
     }
   }
-  return launch_grid_knn<0, false>(h, q, nq, qperm, k, idx, dist, cnt, st);
+  return launch_grid_knn_generic(h, q, nq, qperm, k, idx, dist, cnt, st);
 }
 
 static int bf_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
@@ -899,33 +887,42 @@ static int knn_device(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* i
 }
 
 // ---- radius dispatch -------------------------------------------------------------------------
-template <int D, bool EUCLID>
-static int launch_grid_radius(pomp_nn* h, bool fill, const double* q, int64_t nq, double radius, int inclusive,
-                              int* counts, const int64_t* offsets, int64_t* out, cudaStream_t st) {
+template <int D>
+static int launch_grid_radius_fast(pomp_nn* h, bool fill, const double* q, int64_t nq, double radius, int inclusive,
+                                   int* counts, const int64_t* offsets, int64_t* out, cudaStream_t st) {
   int blocks = (int)((nq + 127) / 128);
   const uint8_t* skip = h->skip_ptr();
   if (fill)
-    LAUNCH((grid_radius_kernel<D, EUCLID, true>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts,
-           (long long)h->n_dev, skip, q, (long long)nq, radius, inclusive, counts, offsets, out);
+    LAUNCH((grid_radius_fast_kernel<D, true>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,
+           (long long)nq, radius, inclusive, counts, offsets, out);
   else
-    LAUNCH((grid_radius_kernel<D, EUCLID, false>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts,
-           (long long)h->n_dev, skip, q, (long long)nq, radius, inclusive, counts, offsets, out);
+    LAUNCH((grid_radius_fast_kernel<D, false>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,
+           (long long)nq, radius, inclusive, counts, offsets, out);
   CHECK_LAUNCH();
   return POMP_OK;
 }
 
 static int grid_radius(pomp_nn* h, bool fill, const double* q, int64_t nq, double radius, int inclusive,
                        int* counts, const int64_t* offsets, int64_t* out, cudaStream_t st) {
-  if (is_plain_euclid(h->metric)) {
+  if (is_plain_euclid(h->metric) && h->grid.G == h->D) {
     switch (h->D) {
-      case 2: return launch_grid_radius<2, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
-      case 3: return launch_grid_radius<3, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
-      case 4: return launch_grid_radius<4, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
-      case 6: return launch_grid_radius<6, true>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      case 2: return launch_grid_radius_fast<2>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      case 3: return launch_grid_radius_fast<3>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      case 4: return launch_grid_radius_fast<4>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+      case 6: return launch_grid_radius_fast<6>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
       default: break;
     }
   }
-  return launch_grid_radius<0, false>(h, fill, q, nq, radius, inclusive, counts, offsets, out, st);
+  int blocks = (int)((nq + 127) / 128);
+  const uint8_t* skip = h->skip_ptr();
+  if (fill)
+    LAUNCH((grid_radius_kernel<0, false, true>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts,
+           (long long)h->n_dev, skip, q, (long long)nq, radius, inclusive, counts, offsets, out);
+  else
+    LAUNCH((grid_radius_kernel<0, false, false>), blocks, 128, 0, st, h->grid, h->metric, h->d_pts,
+           (long long)h->n_dev, skip, q, (long long)nq, radius, inclusive, counts, offsets, out);
+  CHECK_LAUNCH();
+  return POMP_OK;
 }
 
 // offsets: device int64 [nq+1]; returns total through *needed_h (synchronises)

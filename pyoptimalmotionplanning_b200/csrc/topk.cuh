@@ -119,48 +119,39 @@ struct WarpTopK {
   }
 };
 
-// ---- per-thread sorted list (grid search: one query per thread) -----------------------------
-// d[0..k) ascending by (distance, index); slots >= k stay at +inf.  Fully unrolled so the list
-// lives in registers for small K.
+// ---- per-thread sorted list (generic grid search: one query per thread) ----------------------
+// d[0..K) ascending by (distance, index).  Always keeps K entries; a runtime k <= K is served by
+// the first k (the k best are a prefix of the K best).  K <= 32: unrolled, register resident;
+// larger K: rolled loops over a local-memory list.
 template <int K>
 struct ThreadTopK {
-  static constexpr int UNR = K <= 32 ? K : 1;  // big lists live in local memory, loops stay rolled
   double d[K];
   int i[K];
-  int k;  // runtime k <= K
 
-  __device__ __forceinline__ void init(int k_) {
-    k = k_;
-#pragma unroll UNR
-    for (int j = 0; j < K; j++) {
-      d[j] = POMP_INF;
-      i[j] = IDX_NONE;
+  __device__ __forceinline__ void init(int) {
+    if (K <= 32) {
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        d[j] = POMP_INF;
+        i[j] = IDX_NONE;
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < K; j++) {
+        d[j] = POMP_INF;
+        i[j] = IDX_NONE;
+      }
     }
   }
-  __device__ __forceinline__ double threshold() const {
-    if (K == 1) return d[0];
-    double t = d[0];
-#pragma unroll UNR
-    for (int j = 1; j < K; j++)
-      if (j == k - 1) t = d[j];
-    return t;
-  }
-  __device__ __forceinline__ int worst_index() const {
-    if (K == 1) return i[0];
-    int t = i[0];
-#pragma unroll UNR
-    for (int j = 1; j < K; j++)
-      if (j == k - 1) t = i[j];
-    return t;
-  }
-  __device__ __forceinline__ bool full() const { return threshold() < POMP_INF; }
+  __device__ __forceinline__ double threshold() const { return d[K - 1]; }
+  __device__ __forceinline__ bool full() const { return d[K - 1] < POMP_INF; }
   // cheap pre-test before the index is loaded
-  __device__ __forceinline__ bool maybe(double cd) const { return cd < POMP_INF && cd <= threshold(); }
+  __device__ __forceinline__ bool maybe(double cd) const { return cd < POMP_INF && cd <= d[K - 1]; }
   __device__ __forceinline__ void insert(double cd, int ci) {
-    if (!(cd < POMP_INF) || !key_less(cd, ci, threshold(), worst_index())) return;
-#pragma unroll UNR
-    for (int j = K - 1; j >= 1; j--) {
-      if (j <= k - 1) {
+    if (!(cd < POMP_INF) || !key_less(cd, ci, d[K - 1], i[K - 1])) return;
+    if (K <= 32) {
+#pragma unroll
+      for (int j = K - 1; j >= 1; j--) {
         bool lt_prev = key_less(cd, ci, d[j - 1], i[j - 1]);
         bool lt_cur = key_less(cd, ci, d[j], i[j]);
         if (lt_prev) {
@@ -171,12 +162,57 @@ struct ThreadTopK {
           i[j] = ci;
         }
       }
-    }
-    if (key_less(cd, ci, d[0], i[0])) {
-      d[0] = cd;
-      i[0] = ci;
+      if (key_less(cd, ci, d[0], i[0])) {
+        d[0] = cd;
+        i[0] = ci;
+      }
+    } else {
+      int j = K - 1;
+#pragma unroll 1
+      while (j > 0 && key_less(cd, ci, d[j - 1], i[j - 1])) {
+        d[j] = d[j - 1];
+        i[j] = i[j - 1];
+        j--;
+      }
+      d[j] = cd;
+      i[j] = ci;
     }
   }
 };
+
+// in-place ascending sort of one query's hit list (radius queries return hits by insertion index)
+__device__ __forceinline__ void heapsort_i64(int64_t* a, long long n) {
+  if (n < 2) return;
+  for (long long start = n / 2 - 1; start >= 0; start--) {
+    long long root = start;
+    while (true) {
+      long long child = 2 * root + 1;
+      if (child >= n) break;
+      if (child + 1 < n && a[child] < a[child + 1]) child++;
+      if (a[root] >= a[child]) break;
+      int64_t t = a[root];
+      a[root] = a[child];
+      a[child] = t;
+      root = child;
+    }
+  }
+  for (long long end = n - 1; end > 0; end--) {
+    int64_t t = a[0];
+    a[0] = a[end];
+    a[end] = t;
+    long long root = 0;
+    while (true) {
+      long long child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && a[child] < a[child + 1]) child++;
+      if (a[root] >= a[child]) break;
+      int64_t t2 = a[root];
+      a[root] = a[child];
+      a[child] = t2;
+      root = child;
+    }
+  }
+}
+
 
 }  // namespace pomp
