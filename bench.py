@@ -194,6 +194,9 @@ def run_extras(peak):
         pts = torch.from_numpy(gen_points(n, d)).cuda()
         q = torch.from_numpy(gen_queries(nq, d)).cuda()
         nn = CudaNN(MetricSpec.euclidean(d), 0)
+        for name in ("points_per_cell", "block_search", "tile_search", "sort_queries"):
+            if "POMP_" + name.upper() in os.environ:
+                nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
         nn.set_device(pts.data_ptr(), n, st)
         t_build = time_cuda(lambda: nn.build_index(st), reps=2, warm=1)
         out["index_build_D%d" % d] = {"ms": t_build, "points_per_s": n / t_build * 1e3,
@@ -295,6 +298,9 @@ def run_gpu(args):
     q_slice_h = torch.from_numpy(q_all_h[rank * qs:(rank + 1) * qs].copy()).pin_memory()
     pts = torch.from_numpy(pts_h).cuda(local)
     nn = CudaNN(MetricSpec.euclidean(DIM), local)
+    for name in ("points_per_cell", "block_search", "tile_search", "sort_queries"):   # tuning experiments
+        if "POMP_" + name.upper() in os.environ:
+            nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
     nn.set_device(pts.data_ptr(), n, st)
     nn.build_index(st)
     torch.cuda.synchronize()
@@ -393,7 +399,8 @@ def run_gpu(args):
                         "d2h_bytes_per_step": qs * K * 16 * world, "ms_per_step": e2e_s * 1e3,
                         "api": "pomp_nn_nearest_h (pinned host buffers)" if world == 1 else
                                "ShardedNearestNeighbors.knearest + pinned H2D/D2H"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks,
+                "index": {"cells": nn.get_stat("n_cells"), "overflow_queries_last_step": nn.get_stat("overflow_queries")}}
         if world == 1:
             if not args.no_extras:
                 line["extras"] = run_extras(peak)

@@ -193,20 +193,18 @@ __device__ __forceinline__ void scan_tail(const GridDev& g, const double* __rest
   }
 }
 
+// one query through the pruned traversal (phase A + FastLevel recursion + tail)
 template <int D, int K>
-__global__ void __launch_bounds__(128)
-grid_knn_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
-                     const double* __restrict__ q, long long nq, const int* __restrict__ qperm, int k,
-                     int64_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ out_cnt) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nq) return;
-  long long qi = qperm ? (long long)__ldg(qperm + t) : t;
+__device__ __forceinline__ void knn_pruned_one(const GridDev& g, const double* __restrict__ pts, long long n,
+                                               const uint8_t* __restrict__ skip, const double* __restrict__ q,
+                                               long long qi, int k, int64_t* __restrict__ out_idx,
+                                               double* __restrict__ out_dist, int32_t* __restrict__ out_cnt) {
   double qq[D];
   load_point<D>(q, qi, qq);
   PosTopK<K> top;
   top.init(IdxResolver{g.sidx, g.n_indexed});
   // phase A: the query's home cell (its points are close in every coordinate), widened to at
-  // least k sorted-order neighbours; grown further only while masked points leave the list short
+  // least K sorted-order neighbours; grown further only while masked points leave the list short
   long long home = 0;
 #pragma unroll
   for (int a = 0; a < D; a++) home += (long long)grid_cell(g, a, qq[a]) * g.stride[a];
@@ -231,6 +229,222 @@ grid_knn_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, con
   for (int i = 0; i < D; i++) gap[i] = 0.0;
   FastLevel<D, D - 1>::run(g, skip, qq, gap, 0LL, top, w0, w1);
   scan_tail<D>(g, pts, n, skip, qq, top);
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++)
+    if (j < k) {
+      bool fin = top.d[j] < POMP_INF;
+      out_idx[qi * k + j] = fin ? (int64_t)top.res(top.p[j]) : -1;
+      out_dist[qi * k + j] = top.d[j];
+      cnt += fin;
+    }
+  if (out_cnt) out_cnt[qi] = cnt;
+}
+
+// qlist == nullptr: thread t answers query qperm[t] (or t).  qlist != nullptr: grid-stride over the
+// *qcount queries listed there (the block kernel's overflow list).
+template <int D, int K>
+__global__ void __launch_bounds__(128)
+grid_knn_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                     const double* __restrict__ q, long long nq, const int* __restrict__ qperm, int k,
+                     int64_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ out_cnt,
+                     const int* __restrict__ qlist, const int* __restrict__ qcount) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qlist) {
+    long long cnt = *qcount;
+    for (; t < cnt; t += (long long)gridDim.x * blockDim.x)
+      knn_pruned_one<D, K>(g, pts, n, skip, q, (long long)qlist[t], k, out_idx, out_dist, out_cnt);
+    return;
+  }
+  if (t >= nq) return;
+  long long qi = qperm ? (long long)__ldg(qperm + t) : t;
+  knn_pruned_one<D, K>(g, pts, n, skip, q, qi, k, out_idx, out_dist, out_cnt);
+}
+
+// Fixed-block search for 2-D / 3-D: scan the (2R+1)^D block of cells around the home cell (each
+// row of the block is one contiguous run of points), then CERTIFY: if the K-th distance is smaller
+// than the distance from the query to the outside of the block, nothing outside can matter and the
+// answer is exact; otherwise the query goes to the overflow list and is redone by the pruned
+// traversal.  No per-row pruning logic => short, almost divergence-free code for the common case.
+template <int D, int K>
+__global__ void __launch_bounds__(128)
+grid_knn_block_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                      const double* __restrict__ q, long long nq, const int* __restrict__ qperm, int k, int R,
+                      int64_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ out_cnt,
+                      int* __restrict__ ovf_list, int* __restrict__ ovf_count) {
+  static_assert(D == 2 || D == 3, "block kernel is for 2-D and 3-D");
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  long long qi = qperm ? (long long)__ldg(qperm + t) : t;
+  double qq[D];
+  load_point<D>(q, qi, qq);
+  int c[D];
+#pragma unroll
+  for (int a = 0; a < D; a++) c[a] = grid_cell(g, a, qq[a]);
+  PosTopK<K> top;
+  top.init(IdxResolver{g.sidx, g.n_indexed});
+  const int w = 2 * R + 1;
+  const int nrow = (D == 2) ? w : w * w;
+  const int x0 = max(c[0] - R, 0), x1 = min(c[0] + R, g.ncell[0] - 1);
+  for (int r = 0; r < nrow; r++) {
+    int cy = c[1] + (D == 2 ? r : r % w) - R;
+    if (cy < 0 || cy >= g.ncell[1]) continue;
+    long long base = (long long)cy * g.stride[1];
+    if (D == 3) {
+      int cz = c[2] + r / w - R;
+      if (cz < 0 || cz >= g.ncell[2]) continue;
+      base += (long long)cz * g.stride[2];
+    }
+    int s = __ldg(g.cell_start + base + x0), e = __ldg(g.cell_start + base + x1 + 1);
+    scan_run<D>(g, skip, qq, top, s, e);
+  }
+  scan_tail<D>(g, pts, n, skip, qq, top);
+  // certificate: distance from the query to anything bucketed outside the block
+  double margin = POMP_INF;
+#pragma unroll
+  for (int a = 0; a < D; a++) {
+    int lo_c = c[a] - R, hi_c = c[a] + R;
+    if (lo_c > 0) margin = fmin(margin, qq[a] - ((g.lo[a] + (double)lo_c * g.h[a]) + g.slack[a]));
+    if (hi_c < g.ncell[a] - 1) margin = fmin(margin, ((g.lo[a] + (double)(hi_c + 1) * g.h[a]) - g.slack[a]) - qq[a]);
+  }
+  bool exact = !(margin < POMP_INF) || (top.T * (1.0 + 1e-9) < margin);
+  if (!exact) {
+    int o = atomicAdd(ovf_count, 1);
+    ovf_list[o] = (int)qi;
+    return;
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++)
+    if (j < k) {
+      bool fin = top.d[j] < POMP_INF;
+      out_idx[qi * k + j] = fin ? (int64_t)top.res(top.p[j]) : -1;
+      out_dist[qi * k + j] = top.d[j];
+      cnt += fin;
+    }
+  if (out_cnt) out_cnt[qi] = cnt;
+}
+
+// 2-D fixed-block search with the block's rows FLATTENED into one candidate stream: all
+// 2(2R+1) cell_start loads are issued together, then candidates are fetched U at a time
+// (U independent 16-byte loads in flight) -- fewer dependent memory round trips per thread and a
+// single loop whose trip count varies little across the warp.  Returns whether the result is
+// certified exact (same certificate as grid_knn_block_kernel).
+template <int K, int R>
+__device__ __forceinline__ bool flat2d_search(const GridDev& g, const double* __restrict__ pts, long long n,
+                                              const uint8_t* __restrict__ skip, const double (&qq)[2], int cx,
+                                              int cy, PosTopK<K>& top) {
+  constexpr int NR = 2 * R + 1;
+  constexpr int U = 4;
+  const int W = g.ncell[0], H = g.ncell[1];
+  const int x0 = max(cx - R, 0), x1 = min(cx + R, W - 1);
+  int s[NR], pre[NR + 1];
+  pre[0] = 0;
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    int y = cy + r - R;
+    bool valid = y >= 0 && y < H;
+    long long base = (long long)(valid ? y : 0) * W;
+    int ss = __ldg(g.cell_start + base + x0), ee = __ldg(g.cell_start + base + x1 + 1);
+    s[r] = ss;
+    pre[r + 1] = pre[r] + (valid ? ee - ss : 0);
+  }
+  const int total = pre[NR];
+  top.init(IdxResolver{g.sidx, g.n_indexed});
+  const double2* __restrict__ P = reinterpret_cast<const double2*>(g.spts);
+  for (int i = 0; i < total; i += U) {
+    double2 pv[U];
+    int pp[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int ii = min(i + u, total - 1);
+      int pos = s[0] + ii;
+#pragma unroll
+      for (int r = 1; r < NR; r++)
+        if (ii >= pre[r]) pos = s[r] + (ii - pre[r]);
+      pp[u] = pos;
+      pv[u] = __ldg(P + pos);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (i + u < total) {
+        if (skip && skip[__ldg(g.sidx + pp[u])]) continue;
+        double dx = pv[u].x - qq[0], dy = pv[u].y - qq[1];
+        double sq = 0.0;
+        sq = sq + dx * dx;
+        sq = sq + dy * dy;
+        top.offer_sq(sq, pp[u]);
+      }
+    }
+  }
+  scan_tail<2>(g, pts, n, skip, qq, top);
+  double margin = POMP_INF;
+  {
+    int lo_c = cx - R, hi_c = cx + R;
+    if (lo_c > 0) margin = fmin(margin, qq[0] - ((g.lo[0] + (double)lo_c * g.h[0]) + g.slack[0]));
+    if (hi_c < W - 1) margin = fmin(margin, ((g.lo[0] + (double)(hi_c + 1) * g.h[0]) - g.slack[0]) - qq[0]);
+    lo_c = cy - R;
+    hi_c = cy + R;
+    if (lo_c > 0) margin = fmin(margin, qq[1] - ((g.lo[1] + (double)lo_c * g.h[1]) + g.slack[1]));
+    if (hi_c < H - 1) margin = fmin(margin, ((g.lo[1] + (double)(hi_c + 1) * g.h[1]) - g.slack[1]) - qq[1]);
+  }
+  return !(margin < POMP_INF) || (top.T * (1.0 + 1e-9) < margin);
+}
+
+// the rare retry: plain nested loops over a (2R+1)^2 block, R at run time -- no per-row arrays, so
+// it adds code but no registers to the common path
+template <int K>
+__device__ __forceinline__ bool block2d_search_nested(const GridDev& g, const double* __restrict__ pts, long long n,
+                                                      const uint8_t* __restrict__ skip, const double (&qq)[2],
+                                                      int cx, int cy, int R, PosTopK<K>& top) {
+  const int W = g.ncell[0], H = g.ncell[1];
+  const int x0 = max(cx - R, 0), x1 = min(cx + R, W - 1);
+  top.init(IdxResolver{g.sidx, g.n_indexed});
+  for (int y = max(cy - R, 0); y <= min(cy + R, H - 1); y++) {
+    long long base = (long long)y * W;
+    int s = __ldg(g.cell_start + base + x0), e = __ldg(g.cell_start + base + x1 + 1);
+    scan_run<2>(g, skip, qq, top, s, e);
+  }
+  scan_tail<2>(g, pts, n, skip, qq, top);
+  double margin = POMP_INF;
+  int lo_c = cx - R, hi_c = cx + R;
+  if (lo_c > 0) margin = fmin(margin, qq[0] - ((g.lo[0] + (double)lo_c * g.h[0]) + g.slack[0]));
+  if (hi_c < W - 1) margin = fmin(margin, ((g.lo[0] + (double)(hi_c + 1) * g.h[0]) - g.slack[0]) - qq[0]);
+  lo_c = cy - R;
+  hi_c = cy + R;
+  if (lo_c > 0) margin = fmin(margin, qq[1] - ((g.lo[1] + (double)lo_c * g.h[1]) + g.slack[1]));
+  if (hi_c < H - 1) margin = fmin(margin, ((g.lo[1] + (double)(hi_c + 1) * g.h[1]) - g.slack[1]) - qq[1]);
+  return !(margin < POMP_INF) || (top.T * (1.0 + 1e-9) < margin);
+}
+
+// qs != nullptr: queries already gathered in bucket order (coalesced).  An uncertified query is
+// retried once in place with the next larger block (rare: ~exp(-pi*ppc*R^2) of the queries for
+// k=1); only if that fails too does it go to the overflow list for the pruned traversal.
+template <int K, int R>
+__global__ void __launch_bounds__(128)
+grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                       const double* __restrict__ q, const double* __restrict__ qs, long long nq,
+                       const int* __restrict__ qperm, int k, int64_t* __restrict__ out_idx,
+                       double* __restrict__ out_dist, int32_t* __restrict__ out_cnt, int* __restrict__ ovf_list,
+                       int* __restrict__ ovf_count) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  long long qi = qperm ? (long long)__ldg(qperm + t) : t;
+  double qq[2];
+  {
+    double2 v = qs ? __ldg(reinterpret_cast<const double2*>(qs) + t) : __ldg(reinterpret_cast<const double2*>(q) + qi);
+    qq[0] = v.x;
+    qq[1] = v.y;
+  }
+  const int cx = grid_cell(g, 0, qq[0]), cy = grid_cell(g, 1, qq[1]);
+  PosTopK<K> top;
+  bool exact = flat2d_search<K, R>(g, pts, n, skip, qq, cx, cy, top);
+  if (!exact) exact = block2d_search_nested<K>(g, pts, n, skip, qq, cx, cy, R + 1, top);
+  if (!exact) {
+    int o = atomicAdd(ovf_count, 1);
+    ovf_list[o] = (int)qi;
+    return;
+  }
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < K; j++)

@@ -423,23 +423,34 @@ __global__ void cell_scatter_kernel(GridDev g, const double* __restrict__ pts, l
   sidx[pos] = (int)i;
 }
 
-// query ordering by home cell (counting sort with the index's own cells)
-__global__ void query_cell_kernel(GridDev g, const double* __restrict__ q, long long nq, int D,
-                                  int* __restrict__ counts, int* __restrict__ qcell, int* __restrict__ slot) {
+// query ordering by COARSE home bin: bin = (cell row id) * nbx + (axis-0 cell >> shift).  Coarse bins
+// keep the locality (queries of one bin touch the same few KB of sorted points) while the histogram
+// and its scan stay tiny (tens of thousands of bins instead of millions of cells).
+__global__ void query_cell_kernel(GridDev g, const double* __restrict__ q, long long nq, int D, int shift, int nbx,
+                                  int* __restrict__ counts, int* __restrict__ qcell, int* __restrict__ slot,
+                                  int* __restrict__ zero_me) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && zero_me) *zero_me = 0;  // overflow counter of the search that follows
   if (i >= nq) return;
   double p[POMP_MAX_DIM];
   for (int j = 0; j < D; j++) p[j] = q[i * D + j];
-  long long c = grid_cell_id(g, p);
-  qcell[i] = (int)c;
-  slot[i] = atomicAdd(counts + c, 1);
+  int c0 = grid_cell(g, 0, p[g.gdim[0]]);
+  long long row = 0;
+  for (int a = 1; a < g.G; a++) row += (long long)grid_cell(g, a, p[g.gdim[a]]) * (g.stride[a] / g.ncell[0]);
+  long long b = row * nbx + (c0 >> shift);
+  qcell[i] = (int)b;
+  slot[i] = atomicAdd(counts + b, 1);
 }
 
 __global__ void query_perm_kernel(const int* __restrict__ qcell, const int* __restrict__ slot,
-                                  const int* __restrict__ start, long long nq, int* __restrict__ perm) {
+                                  const int* __restrict__ start, const double* __restrict__ q, long long nq, int D,
+                                  int* __restrict__ perm, double* __restrict__ qsorted) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
-  perm[start[qcell[i]] + slot[i]] = (int)i;
+  int t = start[qcell[i]] + slot[i];
+  perm[t] = (int)i;
+  if (qsorted)
+    for (int j = 0; j < D; j++) qsorted[(long long)t * D + j] = q[i * D + j];
 }
 
 // ============================================================================ grid query kernels
@@ -740,24 +751,6 @@ static SplitGeom split_geom(pomp_nn* h, int64_t nq, int64_t n) {
 
 static bool is_plain_euclid(const pomp_metric_desc& m) { return m.kind == POMP_METRIC_EUCLIDEAN && !m.has_cost; }
 
-// ---- optional event timing of the dominant kernel ---------------------------------------------
-static void prof_begin(pomp_nn* h, cudaStream_t st) {
-  if (!h->profile) return;
-  if (h->prof_used + 2 > h->prof_ev.size()) {
-    for (int i = 0; i < 2; i++) {
-      cudaEvent_t e;
-      if (cudaEventCreate(&e) != cudaSuccess) return;
-      h->prof_ev.push_back(e);
-    }
-  }
-  cudaEventRecord(h->prof_ev[h->prof_used], st);
-}
-static void prof_end(pomp_nn* h, cudaStream_t st) {
-  if (!h->profile || h->prof_used + 2 > h->prof_ev.size()) return;
-  cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
-  h->prof_used += 2;
-}
-
 // ---- k-NN dispatch ---------------------------------------------------------------------------
 static int launch_grid_knn_generic(pomp_nn* h, const double* q, int64_t nq, const int* qperm, int k, int64_t* idx,
                                    double* dist, int32_t* cnt, cudaStream_t st) {
@@ -788,7 +781,7 @@ static int launch_grid_knn_fast(pomp_nn* h, const double* q, int64_t nq, const i
   const uint8_t* skip = h->skip_ptr();
 #define GK(KK)                                                                                                 \
   LAUNCH((grid_knn_fast_kernel<D, KK>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, \
-         (long long)nq, qperm, k, idx, dist, cnt)
+         (long long)nq, qperm, k, idx, dist, cnt, (const int*)nullptr, (const int*)nullptr)
   prof_begin(h, st);
   if (k == 1) GK(1);
   else if (k <= 4) GK(4);
@@ -801,30 +794,104 @@ static int launch_grid_knn_fast(pomp_nn* h, const double* q, int64_t nq, const i
   return POMP_OK;
 }
 
+// 2-D / 3-D: fixed block of cells + certificate, overflow redone by the pruned traversal
+template <int D>
+static int launch_grid_knn_block(pomp_nn* h, const double* q, int64_t nq, const int* qperm, int k, int64_t* idx,
+                                 double* dist, int32_t* cnt, cudaStream_t st) {
+  const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
+  // block radius: expect >= ~2.5 K points inside the certified ball of radius R cells
+  double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
+  double vol = D == 2 ? 3.141592653589793 : 4.1887902047863905;
+  int R = 1;
+  while (R < 6 && ppc * vol * pow((double)R, D) < 2.5 * KK + 3.0) R++;
+  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ovf.p;
+  int* ovf_list = h->ovf.p + 1;
+  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  int blocks = (int)((nq + 127) / 128);
+  int oblocks = std::min(blocks, sm_count(h->device) * 4);
+  const uint8_t* skip = h->skip_ptr();
+#define GK(KC)                                                                                                   \
+  do {                                                                                                           \
+    LAUNCH((grid_knn_block_kernel<D, KC>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, \
+           (long long)nq, qperm, k, R, idx, dist, cnt, ovf_list, ovf_count);                                     \
+    prof_end(h, st);                                                                                             \
+    LAUNCH((grid_knn_fast_kernel<D, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, \
+           (long long)nq, (const int*)nullptr, k, idx, dist, cnt, (const int*)ovf_list, (const int*)ovf_count);  \
+  } while (0)
+  prof_begin(h, st);
+  if (KK == 1) GK(1);
+  else if (KK == 4) GK(4);
+  else if (KK == 8) GK(8);
+  else if (KK == 16) GK(16);
+  else GK(32);
+#undef GK
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
 static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
                     cudaStream_t st) {
   const int* qperm = nullptr;
-  if (h->sort_queries != 0 && nq >= 32768 && h->grid.n_cells <= 0x7fffffff) {
-    long long nc = h->grid.n_cells;
-    POMP_TRY(h->counts.reserve((size_t)nc + 1 + (size_t)nc + 1));
+  const double* qsorted = nullptr;
+  const int* qstart = nullptr;
+  const bool fast = is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32;
+  const bool tile = fast && h->D == 2 && h->tile_search != 0;
+  int shift = 0, nbx = h->grid.ncell[0];
+  bool ovf_zeroed = false;
+  if (h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff) {
+    if (h->grid.ncell[0] >= 128) shift = 6;  // 64-cell bins along axis 0 (= the tile kernel's TW)
+    nbx = (h->grid.ncell[0] + (1 << shift) - 1) >> shift;
+    long long nb = (h->grid.n_cells / h->grid.ncell[0]) * nbx;
+    POMP_TRY(h->counts.reserve((size_t)nb + 1 + (size_t)nb + 1));
     POMP_TRY(h->qcell.reserve((size_t)nq * 2));
     POMP_TRY(h->qperm.reserve((size_t)nq));
-    POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(nc)));
+    POMP_TRY(h->ovf.reserve((size_t)nq + 1));
+    if (fast && h->D == 2) POMP_TRY(h->qsorted.reserve((size_t)nq * h->D));
+    POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(nb)));
     int* counts = h->counts.p;
-    int* start = h->counts.p + nc + 1;
-    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nc, st));
+    int* start = h->counts.p + nb + 1;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nb, st));
     int blocks = (int)((nq + 255) / 256);
-    LAUNCH(query_cell_kernel, blocks, 256, 0, st, h->grid, q, (long long)nq, h->D, counts, h->qcell.p,
-           h->qcell.p + nq);
-    POMP_TRY(exclusive_scan<int>(counts, nc, start, h->scan_tmp.p, st));
-    LAUNCH(query_perm_kernel, blocks, 256, 0, st, h->qcell.p, h->qcell.p + nq, start, (long long)nq, h->qperm.p);
+    LAUNCH(query_cell_kernel, blocks, 256, 0, st, h->grid, q, (long long)nq, h->D, shift, nbx, counts, h->qcell.p,
+           h->qcell.p + nq, h->ovf.p);
+    ovf_zeroed = true;
+    if (nb <= 8192) LAUNCH((scan_small_kernel<int>), 1, 1024, 0, st, counts, (int)nb, start);
+    else POMP_TRY(exclusive_scan<int>(counts, nb, start, h->scan_tmp.p, st));
+    LAUNCH(query_perm_kernel, blocks, 256, 0, st, h->qcell.p, h->qcell.p + nq, start, q, (long long)nq, h->D,
+           h->qperm.p, (fast && h->D == 2) ? h->qsorted.p : (double*)nullptr);
     CHECK_LAUNCH();
     qperm = h->qperm.p;
+    qstart = start;
+    if (fast && h->D == 2) qsorted = h->qsorted.p;
   }
-  if (is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32) {
+  h->ovf_zeroed = ovf_zeroed;
+  if (fast) {
+    if (tile && qsorted) {
+      const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
+      double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
+      int R = 1;
+      while (R < 6 && ppc * 3.141592653589793 * R * R < 2.5 * KK + 3.0) R++;
+      if (R <= 3 && shift == 6) {  // 3 = TILE_RMAX (grid_tile.cuh)
+        int rc = launch_grid_knn_tile2d_64(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
+        if (rc <= 0) return rc;
+      }
+    }
     switch (h->D) {
-      case 2: return launch_grid_knn_fast<2>(h, q, nq, qperm, k, idx, dist, cnt, st);
-      case 3: return launch_grid_knn_fast<3>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      case 2: {
+        if (h->block_search != 0) {
+          const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
+          double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
+          int R = 1;
+          while (R < 6 && ppc * 3.141592653589793 * R * R < 2.5 * KK + 3.0) R++;
+          if (R <= 3) return launch_grid_knn_flat2d(h, q, qsorted, nq, qperm, k, R, idx, dist, cnt, st);
+          return launch_grid_knn_block<2>(h, q, nq, qperm, k, idx, dist, cnt, st);
+        }
+        return launch_grid_knn_fast<2>(h, q, nq, qperm, k, idx, dist, cnt, st);
+      }
+      case 3:
+        return h->block_search != 0 ? launch_grid_knn_block<3>(h, q, nq, qperm, k, idx, dist, cnt, st)
+                                    : launch_grid_knn_fast<3>(h, q, nq, qperm, k, idx, dist, cnt, st);
       case 4: return launch_grid_knn_fast<4>(h, q, nq, qperm, k, idx, dist, cnt, st);
       case 6: return launch_grid_knn_fast<6>(h, q, nq, qperm, k, idx, dist, cnt, st);
       default: break;
@@ -1159,6 +1226,9 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   } else if (s == "sort_queries") h->sort_queries = value;
   else if (s == "grid_min_queries") h->grid_min_queries = value;
   else if (s == "max_tail") h->max_tail = value;
+  else if (s == "block_search") h->block_search = value;
+  else if (s == "tile_search") h->tile_search = value;
+  else if (s == "sort_min_queries") h->sort_min_queries = value;
   else if (s == "profile") {
     h->profile = value != 0;
     h->prof_used = 0;
@@ -1183,6 +1253,10 @@ POMP_API int pomp_nn_get_stat(pomp_nn* h, const char* name, double* out) {
       ms += t;
     }
     *out = (s == "search_kernel_ms") ? ms : (double)(h->prof_used / 2);
+  } else if (s == "overflow_queries") {
+    int c = 0;
+    if (h->ovf.p) CUDA_TRY(cudaMemcpy(&c, h->ovf.p, sizeof(int), cudaMemcpyDeviceToHost));
+    *out = (double)c;
   } else if (s == "n_cells") *out = h->grid_valid ? (double)h->grid.n_cells : 0.0;
   else if (s == "n_indexed") *out = h->grid_valid ? (double)h->grid.n_indexed : 0.0;
   else if (s == "grid_axes") *out = h->grid_valid ? (double)h->grid.G : 0.0;

@@ -1,0 +1,95 @@
+// nn_fast2d.cu -- launchers of the 2-D Euclidean large-batch k-NN kernels (the headline path):
+// the flattened fixed-block kernel (grid_fast.cuh) and the streaming TMA tile kernel
+// (grid_tile.cuh), each followed by the overflow pass through the pruned traversal.
+#include "common.cuh"
+#include "grid.cuh"
+#include "grid_fast.cuh"
+#include "grid_tile.cuh"
+#include "nn_handle.cuh"
+#include "topk.cuh"
+
+using namespace pomp;
+
+// 2-D: flattened fixed-block kernel (grid_knn_flat2d_kernel) + overflow pass
+int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm,
+                                  int k, int R, int64_t* idx, double* dist, int32_t* cnt, cudaStream_t st) {
+  const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
+  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ovf.p;
+  int* ovf_list = h->ovf.p + 1;
+  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  int blocks = (int)((nq + 127) / 128);
+  int oblocks = std::min(blocks, sm_count(h->device) * 4);
+  const uint8_t* skip = h->skip_ptr();
+#define GKR(KC, RC)                                                                                              \
+  do {                                                                                                           \
+    LAUNCH((grid_knn_flat2d_kernel<KC, RC>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, \
+           qsorted, (long long)nq, qperm, k, idx, dist, cnt, ovf_list, ovf_count);                               \
+    prof_end(h, st);                                                                                             \
+    LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,  \
+           (long long)nq, (const int*)nullptr, k, idx, dist, cnt, (const int*)ovf_list, (const int*)ovf_count);  \
+  } while (0)
+#define GK(KC)                 \
+  do {                         \
+    if (R == 1) GKR(KC, 1);    \
+    else if (R == 2) GKR(KC, 2); \
+    else GKR(KC, 3);           \
+  } while (0)
+  prof_begin(h, st);
+  if (KK == 1) GK(1);
+  else if (KK == 4) GK(4);
+  else if (KK == 8) GK(8);
+  else if (KK == 16) GK(16);
+  else GK(32);
+#undef GK
+#undef GKR
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+// 2-D Euclidean, bucket-sorted queries: streaming tile kernel (grid_tile.cuh) + overflow pass
+template <int TW>
+static int launch_grid_knn_tile2d(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
+                                  const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist, int32_t* cnt,
+                                  cudaStream_t st) {
+  constexpr int TH = 8;
+  const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
+  double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
+  int cap = (int)(1.5 * (TH + 2 * R) * (TW + 2 * R) * ppc) + 128;
+  size_t smem = (size_t)cap * 16 + sizeof(TileShared<TW, TH>);
+  if (smem > 200 * 1024) return 1;  // caller falls back
+  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ovf.p;
+  int* ovf_list = h->ovf.p + 1;
+  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  const int W = h->grid.ncell[0], H = h->grid.ncell[1];
+  int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+  int oblocks = std::min((int)((nq + 127) / 128), sm_count(h->device) * 4);
+  const uint8_t* skip = h->skip_ptr();
+#define GK(KC)                                                                                                       \
+  do {                                                                                                               \
+    auto kern = grid_knn_tile2d_kernel<KC, TW, TH>;                                                                  \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+    LAUNCH(kern, tiles, 128, smem, st, h->grid, h->d_pts, (long long)h->n_dev, skip, qsorted, qperm, qstart, nbx, k, R, \
+           cap, idx, dist, cnt, ovf_list, ovf_count);                                                                \
+    prof_end(h, st);                                                                                                 \
+    LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,     \
+           (long long)nq, (const int*)nullptr, k, idx, dist, cnt, (const int*)ovf_list, (const int*)ovf_count);      \
+  } while (0)
+  prof_begin(h, st);
+  if (KK == 1) GK(1);
+  else if (KK == 4) GK(4);
+  else if (KK == 8) GK(8);
+  else if (KK == 16) GK(16);
+  else GK(32);
+#undef GK
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+
+int pomp::launch_grid_knn_tile2d_64(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
+                                    const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist,
+                                    int32_t* cnt, cudaStream_t st) {
+  return launch_grid_knn_tile2d<64>(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
+}

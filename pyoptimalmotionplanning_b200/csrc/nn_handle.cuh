@@ -35,8 +35,11 @@ struct pomp_nn {
   double grid_min_points = 16384;
   double points_per_cell = 0;  // 0 = auto by number of grid axes
   double sort_queries = 1;
+  double sort_min_queries = 32768;
   double grid_min_queries = 64;
   double max_tail = 2048;
+  double tile_search = 0;   // 2-D Euclidean, sorted queries: streaming TMA tile kernel (grid_tile.cuh)
+  double block_search = 1;  // 2-D/3-D Euclidean: fixed block of cells + certificate (0: pruned traversal)
   // scratch for queries
   DevBuf<double> q_dev;
   DevBuf<double> part_d;
@@ -44,6 +47,9 @@ struct pomp_nn {
   DevBuf<int> counts;
   DevBuf<int> qperm;
   DevBuf<int> qcell;
+  DevBuf<double> qsorted;
+  bool ovf_zeroed = false;
+  DevBuf<int> ovf;  // [0] = overflow count, [1..] = overflow query ids
   DevBuf<int64_t> out_idx;
   DevBuf<double> out_dist;
   DevBuf<int32_t> out_cnt;
@@ -65,6 +71,25 @@ struct pomp_nn {
 
 
 namespace pomp {
+// ---- optional event timing of the dominant kernel ---------------------------------------------
+inline void prof_begin(pomp_nn* h, cudaStream_t st) {
+  if (!h->profile) return;
+  if (h->prof_used + 2 > h->prof_ev.size()) {
+    for (int i = 0; i < 2; i++) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      h->prof_ev.push_back(e);
+    }
+  }
+  cudaEventRecord(h->prof_ev[h->prof_used], st);
+}
+inline void prof_end(pomp_nn* h, cudaStream_t st) {
+  if (!h->profile || h->prof_used + 2 > h->prof_ev.size()) return;
+  cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
+  h->prof_used += 2;
+}
+
+
 int nn_grow(pomp_nn* h, int64_t need, cudaStream_t st);
 int nn_flush(pomp_nn* h, cudaStream_t st);
 
@@ -78,4 +103,13 @@ struct Mailbox {
   double x[POMP_MAX_DIM];
   double len;
 };
+}  // namespace pomp
+
+namespace pomp {
+// nn_fast2d.cu: 2-D Euclidean large-batch kernels (flattened block kernel, streaming tile kernel)
+int launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm, int k,
+                           int R, int64_t* idx, double* dist, int32_t* cnt, cudaStream_t st);
+int launch_grid_knn_tile2d_64(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
+                              const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist, int32_t* cnt,
+                              cudaStream_t st);
 }  // namespace pomp

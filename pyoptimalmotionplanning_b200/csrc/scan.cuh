@@ -106,6 +106,28 @@ inline int exclusive_scan(const int* in, long long n, OutT* out, long long* tile
   return POMP_OK;
 }
 
+// single-CTA exclusive scan for small arrays (query bins), coalesced: 4 consecutive items per
+// thread per pass, running total carried across passes.  out[n] = grand total
+template <typename OutT>
+__global__ void scan_small_kernel(const int* __restrict__ in, int n, OutT* __restrict__ out) {
+  long long carry = 0;
+  for (int base = 0; base < n; base += blockDim.x * 4) {
+    int i0 = base + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = (i0 + j < n) ? in[i0 + j] : 0;
+    long long s = (long long)v[0] + v[1] + v[2] + v[3];
+    long long tot;
+    long long ex = carry + block_excl_scan(s, &tot);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (i0 + j < n) out[i0 + j] = (OutT)ex;
+      ex += v[j];
+    }
+    carry += tot;
+  }
+  if (threadIdx.x == 0) out[n] = (OutT)carry;
+}
 inline size_t scan_scratch_elems(long long n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1; }
 
 }  // namespace pomp

@@ -314,3 +314,60 @@ def test_errors_are_loud():
         nn.remove(10)
     with pytest.raises(PompError):
         nn.set_mask(np.zeros(3, np.uint8))
+
+
+@pytest.mark.parametrize("k", [1, 4, 16, 32])
+@pytest.mark.parametrize("mode", ["tile", "block", "pruned"])
+def test_large_batch_2d_paths_match_oracle(k, mode):
+    """The bucket-sorted large-batch paths (streaming TMA tile kernel / fixed-block kernel / pruned
+    traversal) against the oracle on a query subset, and against each other on every query."""
+    rng = np.random.default_rng(200 + k)
+    n, nq = 300000, 40000
+    pts = rng.random((n, 2))
+    pts[:20000] = 0.5 + 0.002 * rng.standard_normal((20000, 2))     # a dense cluster: tiles overflow the buffer
+    q = np.concatenate([rng.random((nq - 3000, 2)), 0.5 + 0.004 * rng.standard_normal((2000, 2)),
+                        rng.random((1000, 2)) * 1.2 - 0.1])
+    m = MetricSpec.euclidean(2)
+    nn = _nn(m, pts, grid=True)
+    nn.set_param("tile_search", 1 if mode == "tile" else 0)
+    nn.set_param("block_search", 1 if mode == "block" else 0)
+    idx, dist, cnt = nn.knearest(q, k)
+    sub = rng.choice(nq, 2500, replace=False)
+    oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
+    assert (idx[sub] == oi).all() and (dist[sub] == od).all() and (cnt[sub] == oc).all()
+    ref = _nn(m, pts, grid=True)
+    ref.set_param("sort_queries", 0)
+    ref.set_param("tile_search", 0)
+    ref.set_param("block_search", 0)
+    ridx, rdist, rcnt = ref.knearest(q, k)
+    assert (idx == ridx).all() and (dist == rdist).all()
+
+
+def test_large_batch_3d_block_path_matches_oracle():
+    rng = np.random.default_rng(31)
+    n, nq = 250000, 36000
+    pts = rng.random((n, 3))
+    q = rng.random((nq, 3))
+    m = MetricSpec.euclidean(3)
+    nn = _nn(m, pts, grid=True)
+    for k in (1, 16):
+        idx, dist, cnt = nn.knearest(q, k)
+        sub = rng.choice(nq, 1500, replace=False)
+        oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
+        assert (idx[sub] == oi).all() and (dist[sub] == od).all()
+
+
+def test_tile_path_with_masks_and_tail():
+    rng = np.random.default_rng(32)
+    m = MetricSpec.euclidean(2)
+    pts = rng.random((120000, 2))
+    q = rng.random((33000, 2))
+    nn = _nn(m, pts[:119000], grid=True)
+    nn.build_index()
+    nn.add(pts[119000:])
+    mask = (rng.random(120000) < 0.2).astype(np.uint8)
+    nn.set_mask(mask)
+    idx, dist, cnt = nn.knearest(q, 4)
+    sub = rng.choice(33000, 1500, replace=False)
+    oi, od, oc = oracle.nn_knearest(m, pts, q[sub], 4, mask)
+    assert (idx[sub] == oi).all() and (dist[sub] == od).all()
