@@ -194,7 +194,7 @@ def run_extras(peak):
         pts = torch.from_numpy(gen_points(n, d)).cuda()
         q = torch.from_numpy(gen_queries(nq, d)).cuda()
         nn = CudaNN(MetricSpec.euclidean(d), 0)
-        for name in ("points_per_cell", "block_search", "tile_search", "sort_queries"):
+        for name in ("points_per_cell", "block_search", "tile_search", "sort_queries", "sort_shift"):
             if "POMP_" + name.upper() in os.environ:
                 nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
         nn.set_device(pts.data_ptr(), n, st)
@@ -298,7 +298,7 @@ def run_gpu(args):
     q_slice_h = torch.from_numpy(q_all_h[rank * qs:(rank + 1) * qs].copy()).pin_memory()
     pts = torch.from_numpy(pts_h).cuda(local)
     nn = CudaNN(MetricSpec.euclidean(DIM), local)
-    for name in ("points_per_cell", "block_search", "tile_search", "sort_queries"):   # tuning experiments
+    for name in ("points_per_cell", "block_search", "tile_search", "sort_queries", "sort_shift"):   # tuning experiments
         if "POMP_" + name.upper() in os.environ:
             nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
     nn.set_device(pts.data_ptr(), n, st)

@@ -10,6 +10,8 @@
 //     survives is compared on the rooted value exactly as the reference does (vectorops.py:101).
 #pragma once
 #include "grid.cuh"
+#include <type_traits>
+
 #include "topk.cuh"
 
 namespace pomp {
@@ -78,6 +80,95 @@ struct PosTopK {
     T = d[K - 1];
     tsq = tsq_of(T);
   }
+  __device__ __forceinline__ void finish(int (&idx)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; j++) idx[j] = p[j] >= 0 ? res(p[j]) : IDX_NONE;
+  }
+};
+
+// Larger k: keep the K best UNSORTED and track the worst kept entry (what KNearestResult does,
+// knn.py:14-23): an insertion is "overwrite the worst slot, rescan for the new worst" (~3 ops per
+// slot) instead of a shifting sorted insert (~12 per slot); one sort at the very end.
+template <int K>
+struct PosMaxK {
+  static_assert(K <= 32, "register-resident list");
+  double d[K];
+  int p[K];
+  double T, tsq;  // worst kept distance (+inf while slots are free) and its squared prune bound
+  int wp;         // position of the worst kept entry (-1: a free slot)
+  int wslot;
+  IdxResolver res;
+
+  __device__ __forceinline__ void init(IdxResolver r) {
+    res = r;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      d[j] = POMP_INF;
+      p[j] = -1;
+    }
+    T = POMP_INF;
+    tsq = POMP_INF;
+    wp = -1;
+    wslot = 0;
+  }
+  __device__ __forceinline__ double threshold() const { return T; }
+  __device__ __forceinline__ double tsq_up() const { return tsq; }
+  __device__ __forceinline__ bool full() const { return T < POMP_INF; }
+  __device__ __forceinline__ void offer_sq(double s, int pos) {
+    if (!(s <= tsq)) return;
+    double cd = sqrt(s);
+    if (!(cd < POMP_INF)) return;
+    // must beat the worst kept entry on (distance, insertion index)
+    if (!(cd < T)) {
+      if (!(cd == T && wp >= 0 && res(pos) < res(wp))) return;
+    }
+#pragma unroll
+    for (int j = 0; j < K; j++)
+      if (j == wslot) {
+        d[j] = cd;
+        p[j] = pos;
+      }
+    // new worst
+    double wd = d[0];
+    int wq = p[0], ws = 0;
+#pragma unroll
+    for (int j = 1; j < K; j++) {
+      bool worse = d[j] > wd;
+      if (d[j] == wd && d[j] < POMP_INF) worse = res(p[j]) > res(wq);
+      if (worse) {
+        wd = d[j];
+        wq = p[j];
+        ws = j;
+      }
+    }
+    T = wd;
+    wp = wq;
+    wslot = ws;
+    tsq = tsq_of(T);
+  }
+  // sort by (distance, insertion index); idx[] receives the resolved indices
+  __device__ __forceinline__ void finish(int (&idx)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; j++) idx[j] = p[j] >= 0 ? res(p[j]) : IDX_NONE;
+#pragma unroll
+    for (int a = 0; a < K; a++) {
+#pragma unroll
+      for (int b = (a & 1); b + 1 < K; b += 2) {  // odd-even transposition sort: K passes, branch-free
+        bool sw = d[b] > d[b + 1] || (d[b] == d[b + 1] && idx[b] > idx[b + 1]);
+        double td = sw ? d[b + 1] : d[b], ud = sw ? d[b] : d[b + 1];
+        int ti = sw ? idx[b + 1] : idx[b], ui = sw ? idx[b] : idx[b + 1];
+        d[b] = td;
+        d[b + 1] = ud;
+        idx[b] = ti;
+        idx[b + 1] = ui;
+      }
+    }
+  }
+};
+
+template <int K>
+struct BestList {  // sorted insertion for tiny k, worst-tracking for the rest
+  using type = typename std::conditional<(K <= 4), PosTopK<K>, PosMaxK<K>>::type;
 };
 
 // fixed-radius collector (count or fill)
@@ -330,10 +421,10 @@ grid_knn_block_kernel(GridDev g, const double* __restrict__ pts, long long n, co
 // (U independent 16-byte loads in flight) -- fewer dependent memory round trips per thread and a
 // single loop whose trip count varies little across the warp.  Returns whether the result is
 // certified exact (same certificate as grid_knn_block_kernel).
-template <int K, int R>
+template <int K, int R, class L>
 __device__ __forceinline__ bool flat2d_search(const GridDev& g, const double* __restrict__ pts, long long n,
                                               const uint8_t* __restrict__ skip, const double (&qq)[2], int cx,
-                                              int cy, PosTopK<K>& top) {
+                                              int cy, L& top) {
   constexpr int NR = 2 * R + 1;
   constexpr int U = 4;
   const int W = g.ncell[0], H = g.ncell[1];
@@ -342,7 +433,8 @@ __device__ __forceinline__ bool flat2d_search(const GridDev& g, const double* __
   pre[0] = 0;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
-    int y = cy + r - R;
+    // centre row first, then alternately below/above: near candidates tighten the bound early
+    int y = cy + ((r & 1) ? -((r + 1) >> 1) : (r >> 1));
     bool valid = y >= 0 && y < H;
     long long base = (long long)(valid ? y : 0) * W;
     int ss = __ldg(g.cell_start + base + x0), ee = __ldg(g.cell_start + base + x1 + 1);
@@ -393,10 +485,10 @@ __device__ __forceinline__ bool flat2d_search(const GridDev& g, const double* __
 
 // the rare retry: plain nested loops over a (2R+1)^2 block, R at run time -- no per-row arrays, so
 // it adds code but no registers to the common path
-template <int K>
+template <int K, class L>
 __device__ __forceinline__ bool block2d_search_nested(const GridDev& g, const double* __restrict__ pts, long long n,
                                                       const uint8_t* __restrict__ skip, const double (&qq)[2],
-                                                      int cx, int cy, int R, PosTopK<K>& top) {
+                                                      int cx, int cy, int R, L& top) {
   const int W = g.ncell[0], H = g.ncell[1];
   const int x0 = max(cx - R, 0), x1 = min(cx + R, W - 1);
   top.init(IdxResolver{g.sidx, g.n_indexed});
@@ -437,7 +529,7 @@ grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
     qq[1] = v.y;
   }
   const int cx = grid_cell(g, 0, qq[0]), cy = grid_cell(g, 1, qq[1]);
-  PosTopK<K> top;
+  typename BestList<K>::type top;
   bool exact = flat2d_search<K, R>(g, pts, n, skip, qq, cx, cy, top);
   if (!exact) exact = block2d_search_nested<K>(g, pts, n, skip, qq, cx, cy, R + 1, top);
   if (!exact) {
@@ -445,12 +537,14 @@ grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
     ovf_list[o] = (int)qi;
     return;
   }
+  int idx[K];
+  top.finish(idx);
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < K; j++)
     if (j < k) {
       bool fin = top.d[j] < POMP_INF;
-      out_idx[qi * k + j] = fin ? (int64_t)top.res(top.p[j]) : -1;
+      out_idx[qi * k + j] = fin ? (int64_t)idx[j] : -1;
       out_dist[qi * k + j] = top.d[j];
       cnt += fin;
     }

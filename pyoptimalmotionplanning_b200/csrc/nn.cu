@@ -666,7 +666,7 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
     set_error("metric/point set gives no usable grid axis");
     return POMP_ERR_INVALID;
   }
-  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G <= 2 ? 4.0 : (G == 3 ? 8.0 : 16.0));
+  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G <= 3 ? 2.0 : 16.0);  // measured on B200, bench extras
   double target = fmax(1.0, (double)n / ppc);
   target = fmin(target, 268435456.0);
   // cubic cells in metric space: ncell_a proportional to the weighted extent
@@ -840,7 +840,7 @@ static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx
   int shift = 0, nbx = h->grid.ncell[0];
   bool ovf_zeroed = false;
   if (h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff) {
-    if (h->grid.ncell[0] >= 128) shift = 6;  // 64-cell bins along axis 0 (= the tile kernel's TW)
+    if (h->grid.ncell[0] >= 128) shift = (int)h->sort_shift;  // 2^shift-cell bins along axis 0 (6 = the tile kernel's TW)
     nbx = (h->grid.ncell[0] + (1 << shift) - 1) >> shift;
     long long nb = (h->grid.n_cells / h->grid.ncell[0]) * nbx;
     POMP_TRY(h->counts.reserve((size_t)nb + 1 + (size_t)nb + 1));
@@ -1229,6 +1229,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "block_search") h->block_search = value;
   else if (s == "tile_search") h->tile_search = value;
   else if (s == "sort_min_queries") h->sort_min_queries = value;
+  else if (s == "sort_shift") h->sort_shift = value;
   else if (s == "profile") {
     h->profile = value != 0;
     h->prof_used = 0;

@@ -36,6 +36,7 @@ struct pomp_nn {
   double points_per_cell = 0;  // 0 = auto by number of grid axes
   double sort_queries = 1;
   double sort_min_queries = 32768;
+  double sort_shift = 6;
   double grid_min_queries = 64;
   double max_tail = 2048;
   double tile_search = 0;   // 2-D Euclidean, sorted queries: streaming TMA tile kernel (grid_tile.cuh)
