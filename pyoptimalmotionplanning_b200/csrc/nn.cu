@@ -1088,6 +1088,9 @@ POMP_API int pomp_nn_destroy(pomp_nn* h) {
   if (h->ticket) cudaFree(h->ticket);
   if (h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
   delete h;
   return POMP_OK;
 }
@@ -1230,6 +1233,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "tile_search") h->tile_search = value;
   else if (s == "sort_min_queries") h->sort_min_queries = value;
   else if (s == "sort_shift") h->sort_shift = value;
+  else if (s == "pipeline_chunks") h->pipeline_chunks = value;
   else if (s == "profile") {
     h->profile = value != 0;
     h->prof_used = 0;
@@ -1299,6 +1303,50 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
   POMP_TRY(h->out_idx.reserve((size_t)nq * k));
   POMP_TRY(h->out_dist.reserve((size_t)nq * k));
   POMP_TRY(h->out_cnt.reserve((size_t)nq));
+  // Large batches: software pipeline over chunks -- H2D of chunk c+1 (copy-in stream), search of
+  // chunk c (compute stream, scratch reused in order) and D2H of chunk c-1 (copy-out stream) overlap,
+  // so PCIe runs in both directions while the SMs work.  Small batches: one pass on one stream.
+  const int64_t kMinPipelined = 131072;
+  int nchunk = (nq >= kMinPipelined && h->pipeline_chunks > 1) ? (int)h->pipeline_chunks : 1;
+  if (nchunk > 1) {
+    POMP_TRY(nn_flush(h, st));
+    bool use_grid = false;
+    POMP_TRY(want_grid(h, nq, &use_grid, st));  // build / refresh the index once, before the pipeline
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!h->copy_in) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    }
+    while ((int)h->pipe_ev.size() < 2 * nchunk) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->pipe_ev.push_back(e);
+    }
+    int64_t per = ((nq + nchunk - 1) / nchunk + 127) / 128 * 128;
+    for (int c = 0; c < nchunk; c++) {
+      int64_t b = (int64_t)c * per, e = std::min<int64_t>(nq, b + per);
+      if (b >= e) break;
+      int64_t m = e - b;
+      CUDA_TRY(cudaMemcpyAsync(h->q_dev.p + b * h->D, q_h + b * h->D, sizeof(double) * (size_t)m * h->D,
+                               cudaMemcpyHostToDevice, h->copy_in));
+      CUDA_TRY(cudaEventRecord(h->pipe_ev[2 * c], h->copy_in));
+      CUDA_TRY(cudaStreamWaitEvent(st, h->pipe_ev[2 * c], 0));
+      POMP_TRY(knn_device(h, h->q_dev.p + b * h->D, m, k, h->out_idx.p + b * k, h->out_dist.p + b * k,
+                          count_h ? h->out_cnt.p + b : nullptr, st));
+      CUDA_TRY(cudaEventRecord(h->pipe_ev[2 * c + 1], st));
+      CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->pipe_ev[2 * c + 1], 0));
+      CUDA_TRY(cudaMemcpyAsync(idx_h + b * k, h->out_idx.p + b * k, sizeof(int64_t) * (size_t)m * k,
+                               cudaMemcpyDeviceToHost, h->copy_out));
+      CUDA_TRY(cudaMemcpyAsync(dist_h + b * k, h->out_dist.p + b * k, sizeof(double) * (size_t)m * k,
+                               cudaMemcpyDeviceToHost, h->copy_out));
+      if (count_h)
+        CUDA_TRY(cudaMemcpyAsync(count_h + b, h->out_cnt.p + b, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost,
+                                 h->copy_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->copy_out));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return POMP_OK;
+  }
   CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, q_h, sizeof(double) * (size_t)nq * h->D, cudaMemcpyHostToDevice, st));
   POMP_TRY(knn_device(h, h->q_dev.p, nq, k, h->out_idx.p, h->out_dist.p, count_h ? h->out_cnt.p : nullptr, st));
   CUDA_TRY(cudaMemcpyAsync(idx_h, h->out_idx.p, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));

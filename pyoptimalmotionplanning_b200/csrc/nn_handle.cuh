@@ -60,6 +60,9 @@ struct pomp_nn {
   void* mailbox_d = nullptr;
   unsigned int* ticket = nullptr;
   cudaStream_t stream = nullptr;  // used by the *_h variants
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined *_h path
+  std::vector<cudaEvent_t> pipe_ev;
+  double pipeline_chunks = 4;
   // optional timing of the dominant search kernel with CUDA events on the launching stream
   // (bench.py's roofline numerator); enabled with set_param("profile", 1)
   bool profile = false;

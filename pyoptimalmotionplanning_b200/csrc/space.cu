@@ -52,6 +52,113 @@ __device__ __forceinline__ bool edge_linear(const SpaceDev& s, const double* a, 
   return true;
 }
 
+// ---- 2-D linear edges, warp-cooperative --------------------------------------------------------
+// EpsilonEdgeChecker's result is a pure conjunction over the endpoints and the k interior samples,
+// so the samples may be evaluated in any order.  Thread-per-edge evaluation leaves ~3 of 32 lanes
+// busy on obstacle-dense roadmaps (edges die at different samples); here a warp takes 32 edges,
+// checks all endpoints at once, then lays the interior samples of the surviving edges out as one
+// item queue (edge-major) and evaluates 32 items per round, one per lane.
+__device__ __forceinline__ int warp_incl_scan_i(int v) {
+  int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ bool edge_batch_warp2d(const SpaceDev& s, double2 a, double2 b, bool valid, double res,
+                                                  unsigned* failbits /* one word per warp, shared */) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double pa[2] = {a.x, a.y}, pb[2] = {b.x, b.y};
+  double t0 = pa[0] - pb[0], t1 = pa[1] - pb[1];
+  double l = 0.0;
+  l = l + t0 * t0;
+  l = l + t1 * t1;
+  l = sqrt(l);
+  long long k = edge_samples(l, res);
+  bool alive = valid && feasible_pt(s, pa) && feasible_pt(s, pb);
+  const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
+  bool big = k > 4096;  // pathological resolution: this lane walks its own edge afterwards
+  int cnt = (alive && !big) ? (int)k : 0;
+  int incl = warp_incl_scan_i(cnt);
+  int excl = incl - cnt;
+  int total = __shfl_sync(FULL, incl, 31);
+  if (lane == 0) *failbits = 0u;
+  __syncwarp();
+  for (int base = 0; base < total; base += 32) {
+    int j = base + lane;
+    int owner = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      int cand = owner + step;
+      int ce = __shfl_sync(FULL, excl, cand & 31);
+      if (cand < 32 && ce <= j) owner = cand;
+    }
+    int oe = __shfl_sync(FULL, excl, owner);
+    int ok_ = __shfl_sync(FULL, cnt, owner);
+    double ax = __shfl_sync(FULL, pa[0], owner), ay = __shfl_sync(FULL, pa[1], owner);
+    double ddx = __shfl_sync(FULL, dx, owner), ddy = __shfl_sync(FULL, dy, owner);
+    unsigned fb = *(volatile unsigned*)failbits;
+    bool act = j < total && !((fb >> owner) & 1u);
+    if (act) {
+      int i = j - oe;
+      double u = (double)(i + 1) / (double)(ok_ + 2);
+      double x[2] = {ax + u * ddx, ay + u * ddy};
+      if (!feasible_pt(s, x)) atomicOr(failbits, 1u << owner);
+    }
+    __syncwarp();
+  }
+  bool fail = ((*(volatile unsigned*)failbits) >> lane) & 1u;
+  __syncwarp();
+  bool okv = alive && !fail;
+  if (okv && big) {
+    const double kk2 = (double)(k + 2);
+    for (long long i = 0; i < k; i++) {
+      double u = (double)(i + 1) / kk2;
+      double x[2] = {pa[0] + u * dx, pa[1] + u * dy};
+      if (!feasible_pt(s, x)) {
+        okv = false;
+        break;
+      }
+    }
+  }
+  return okv;
+}
+
+__global__ void __launch_bounds__(128)
+edge_check_warp2d_kernel(SpaceDev s, const double* __restrict__ a, const double* __restrict__ b, long long n,
+                         double res, uint8_t* __restrict__ ok) {
+  __shared__ unsigned failbits[4];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i < n;
+  double2 va = make_double2(0, 0), vb = make_double2(0, 0);
+  if (valid) {
+    va = __ldg(reinterpret_cast<const double2*>(a) + i);
+    vb = __ldg(reinterpret_cast<const double2*>(b) + i);
+  }
+  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5]);
+  if (valid) ok[i] = r ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(128)
+edge_check_indexed_warp2d_kernel(SpaceDev s, const double* __restrict__ nodes, const int* __restrict__ ij,
+                                 long long n, double res, uint8_t* __restrict__ ok) {
+  __shared__ unsigned failbits[4];
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = e < n;
+  double2 va = make_double2(0, 0), vb = make_double2(0, 0);
+  if (valid) {
+    int2 pr = __ldg(reinterpret_cast<const int2*>(ij) + e);
+    va = __ldg(reinterpret_cast<const double2*>(nodes) + pr.x);
+    vb = __ldg(reinterpret_cast<const double2*>(nodes) + pr.y);
+  }
+  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5]);
+  if (valid) ok[e] = r ? 1 : 0;
+}
+
 template <int D>
 __global__ void edge_check_kernel(SpaceDev s, const double* __restrict__ a, const double* __restrict__ b,
                                   long long n, double res, uint8_t* __restrict__ ok) {
@@ -409,7 +516,7 @@ POMP_API int pomp_edge_check(pomp_space* sp, const double* a, const double* b, i
   if (n == 0) return POMP_OK;
   int blocks = (int)((n + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
-  if (sp->dev.dim == 2) LAUNCH((edge_check_kernel<2>), blocks, 128, 0, st, sp->dev, a, b, (long long)n, resolution, ok);
+  if (sp->dev.dim == 2) LAUNCH(edge_check_warp2d_kernel, blocks, 128, 0, st, sp->dev, a, b, (long long)n, resolution, ok);
   else LAUNCH((edge_check_kernel<0>), blocks, 128, 0, st, sp->dev, a, b, (long long)n, resolution, ok);
   CHECK_LAUNCH();
   return POMP_OK;
@@ -425,7 +532,7 @@ POMP_API int pomp_edge_check_indexed(pomp_space* sp, const double* nodes, const 
   int blocks = (int)((n_edges + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   if (sp->dev.dim == 2)
-    LAUNCH((edge_check_indexed_kernel<2>), blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok);
+    LAUNCH(edge_check_indexed_warp2d_kernel, blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok);
   else
     LAUNCH((edge_check_indexed_kernel<0>), blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok);
   CHECK_LAUNCH();
