@@ -29,15 +29,15 @@ __device__ __forceinline__ double tsq_of(double T) { return (T * T) * (1.0 + 0x1
 // The list always keeps K entries (a runtime k <= K is served by its first k entries: the k best
 // are a prefix of the K best).  No runtime slot arithmetic: with it, LLVM folds the unrolled
 // selects back into a dynamically indexed local array and the list leaves the register file.
-template <int K>
+template <int K, class Res = IdxResolver>
 struct PosTopK {
   static_assert(K <= 32, "register-resident list: larger k goes through the generic kernel");
   double d[K];
   int p[K];
   double T, tsq;  // current K-th distance and its squared prune bound
-  IdxResolver res;
+  Res res;
 
-  __device__ __forceinline__ void init(IdxResolver r) {
+  __device__ __forceinline__ void init(Res r) {
     res = r;
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -89,7 +89,7 @@ struct PosTopK {
 // Larger k: keep the K best UNSORTED and track the worst kept entry (what KNearestResult does,
 // knn.py:14-23): an insertion is "overwrite the worst slot, rescan for the new worst" (~3 ops per
 // slot) instead of a shifting sorted insert (~12 per slot); one sort at the very end.
-template <int K>
+template <int K, class Res = IdxResolver>
 struct PosMaxK {
   static_assert(K <= 32, "register-resident list");
   double d[K];
@@ -97,9 +97,9 @@ struct PosMaxK {
   double T, tsq;  // worst kept distance (+inf while slots are free) and its squared prune bound
   int wp;         // position of the worst kept entry (-1: a free slot)
   int wslot;
-  IdxResolver res;
+  Res res;
 
-  __device__ __forceinline__ void init(IdxResolver r) {
+  __device__ __forceinline__ void init(Res r) {
     res = r;
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -166,9 +166,9 @@ struct PosMaxK {
   }
 };
 
-template <int K>
+template <int K, class Res = IdxResolver>
 struct BestList {  // sorted insertion for tiny k, worst-tracking for the rest
-  using type = typename std::conditional<(K <= 4), PosTopK<K>, PosMaxK<K>>::type;
+  using type = typename std::conditional<(K <= 4), PosTopK<K, Res>, PosMaxK<K, Res>>::type;
 };
 
 // fixed-radius collector (count or fill)

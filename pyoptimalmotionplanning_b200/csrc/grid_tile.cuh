@@ -209,4 +209,302 @@ grid_knn_tile2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
   }
 }
 
+// =====================================================================================================
+// Persistent, warp-specialised streaming kernel (the headline path).
+//
+// One CTA per SM loops over tiles of TW x TH cells.  A PRODUCER warp runs ahead: for each tile it
+// reads the few cell_start / qstart entries that bound the tile's halo rows and query ranges, then
+// issues cp.async.bulk (TMA) copies -- the halo rows of the bucket-sorted point array, the matching
+// slices of cell_start and the tile's bucket-sorted queries -- into one stage of a shared-memory
+// ring; all copies of a stage complete on its `full` mbarrier.  Two CONSUMER groups (4 warps each)
+// alternate tiles: one query per thread, searched entirely in shared memory (flattened (2R+1)^2
+// block + certificate, like grid_knn_flat2d_kernel), then `empty` is signalled and the producer
+// refills the stage.  HBM therefore sees a continuous stream of multi-KB sequential reads kept in
+// flight by the ring, independent of the consumers' latency.
+// =====================================================================================================
+// candidates of the streaming kernel are identified by their slot in the stage's sidx slice; points
+// appended after the index build (never staged) carry their insertion index with a tag bit
+struct StageResolver {
+  const int* ssidx;
+  __device__ __forceinline__ int operator()(int p) const { return (p & 0x40000000) ? (p & 0x3fffffff) : ssidx[p]; }
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int ST_TW = 64;             // tile width in cells = query-sort bin width (shift 6)
+constexpr int ST_TH = 8;              // tile height in cell rows
+constexpr int ST_ROWS = ST_TH + 2 * TILE_RMAX;
+constexpr int ST_CSW = ST_TW + 16;    // cell_start ints copied per halo row (16-byte aligned slices)
+constexpr int ST_STAGES = 5;
+constexpr int ST_PROD_WARPS = 4;      // producers take tiles round-robin: 4 metadata round trips in flight
+constexpr int ST_CONS_WARPS = 12;     // consumer warp pool
+constexpr int ST_SLOTS = 5;           // 32-query chunk slots per tile (cap_q <= 160)
+constexpr int ST_THREADS = 32 * (ST_PROD_WARPS + ST_CONS_WARPS);
+
+struct StreamHeader {
+  int nq, fits, nrows, ylo, xal, tx0, ty0, tx1, ty1, pad;
+  int row_gs[ST_ROWS];   // first sorted position of each halo row
+  int row_off[ST_ROWS];  // offset of the row in the stage's point buffer
+  int qbeg[ST_TH];       // first sorted query of each tile row
+  int qpre[ST_TH + 1];   // prefix of per-row query counts (= offset in the stage's query buffer)
+  int row_ioff[ST_ROWS]; // sidx slice of halo row r starts at ssidx[row_ioff[r]] and holds sidx[row_gs[r] & ~3 ...]
+  int qp_off[ST_TH];     // qperm slice of tile row r starts at sqperm[qp_off[r]] and holds qperm[qbeg[r] & ~3 ...]
+};
+
+struct StreamLayout {  // byte offsets inside one stage
+  int cap_pts, cap_q;
+  int off_pts, off_cs, off_q, off_sidx, off_qperm, off_hdr, stage_bytes;
+};
+
+__host__ __device__ inline StreamLayout stream_layout(int cap_pts, int cap_q) {
+  StreamLayout L;
+  L.cap_pts = cap_pts;
+  L.cap_q = cap_q;
+  L.off_pts = 0;
+  L.off_cs = L.off_pts + cap_pts * 16;
+  L.off_q = L.off_cs + ST_ROWS * ST_CSW * 4;
+  L.off_sidx = L.off_q + cap_q * 16;                       // per halo row: aligned slice of sidx (+3 slack each)
+  L.off_qperm = L.off_sidx + (cap_pts + 8 * ST_ROWS) * 4;  // per tile row: aligned slice of qperm
+  L.off_hdr = L.off_qperm + (cap_q + 8 * ST_TH) * 4;
+  L.stage_bytes = (L.off_hdr + (int)sizeof(StreamHeader) + 127) / 128 * 128;
+  return L;
+}
+
+template <int K>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+grid_knn_stream2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                         const double* __restrict__ qs, const int* __restrict__ qperm,
+                         const int* __restrict__ qstart, int nbx, int k, int R, int cap_pts, int cap_q,
+                         int64_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ out_cnt,
+                         int* __restrict__ ovf_list, int* __restrict__ ovf_count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const StreamLayout L = stream_layout(cap_pts, cap_q);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [ST_STAGES]
+  uint64_t* empty = full + ST_STAGES;                      // [ST_STAGES]
+  unsigned char* stages = smem_raw + 128;
+
+  const int W = g.ncell[0], H = g.ncell[1];
+  const int ntx = (W + ST_TW - 1) / ST_TW, nty = (H + ST_TH - 1) / ST_TH;
+  const int ntiles = ntx * nty;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ST_CONS_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp < ST_PROD_WARPS) {
+    // ------------------------------------------------------------------ producers
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      if (it % ST_PROD_WARPS != warp) continue;
+      const int s = it % ST_STAGES;
+      if (it >= ST_STAGES) mbar_wait(&empty[s], ((it / ST_STAGES) - 1) & 1);
+      unsigned char* st = stages + (size_t)s * L.stage_bytes;
+      StreamHeader* hd = reinterpret_cast<StreamHeader*>(st + L.off_hdr);
+      const int tcol = tile % ntx;
+      const int tx0 = tcol * ST_TW, ty0 = (tile / ntx) * ST_TH;
+      const int tx1 = min(tx0 + ST_TW, W) - 1, ty1 = min(ty0 + ST_TH, H) - 1;
+      const int xlo = max(tx0 - R, 0), xhi = min(tx1 + R, W - 1);
+      const int ylo = max(ty0 - R, 0), yhi = min(ty1 + R, H - 1);
+      const int nrows = yhi - ylo + 1;
+      const int xal = max(tx0 - 4, 0);
+      // query ranges of the tile rows (lanes 0..TH-1) and point ranges of the halo rows (lanes 0..nrows-1)
+      int qb = 0, qn = 0;
+      if (lane < ST_TH && ty0 + lane <= ty1) {
+        qb = __ldg(qstart + (long long)(ty0 + lane) * nbx + tcol);
+        qn = __ldg(qstart + (long long)(ty0 + lane) * nbx + tcol + 1) - qb;
+      }
+      int gs = 0, gn = 0;
+      if (lane < nrows) {
+        gs = __ldg(g.cell_start + (long long)(ylo + lane) * W + xlo);
+        gn = __ldg(g.cell_start + (long long)(ylo + lane) * W + xhi + 1) - gs;
+      }
+      int qincl = qn, gincl = gn;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int a = __shfl_up_sync(0xffffffffu, qincl, o), b = __shfl_up_sync(0xffffffffu, gincl, o);
+        if (lane >= o) {
+          qincl += a;
+          gincl += b;
+        }
+      }
+      const int nq = __shfl_sync(0xffffffffu, qincl, 31), npts = __shfl_sync(0xffffffffu, gincl, 31);
+      // 16-byte aligned slices of the 4-byte arrays (sidx per halo row, qperm per tile row)
+      const int gal = gs & ~3, galn = gn > 0 ? (((gs + gn + 3) & ~3) - gal) : 0;
+      const int qal = qb & ~3, qaln = qn > 0 ? (((qb + qn + 3) & ~3) - qal) : 0;
+      int iincl = galn, pincl = qaln;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int a = __shfl_up_sync(0xffffffffu, iincl, o), b = __shfl_up_sync(0xffffffffu, pincl, o);
+        if (lane >= o) {
+          iincl += a;
+          pincl += b;
+        }
+      }
+      const int nidx = __shfl_sync(0xffffffffu, iincl, 31), nqp = __shfl_sync(0xffffffffu, pincl, 31);
+      const bool fits = npts <= cap_pts && nq <= cap_q && nidx <= cap_pts + 8 * ST_ROWS && nqp <= cap_q + 8 * ST_TH;
+      if (lane < ST_TH) {
+        hd->qbeg[lane] = qb;
+        hd->qpre[lane] = qincl - qn;
+        hd->qp_off[lane] = pincl - qaln;
+      }
+      if (lane == ST_TH) hd->qpre[ST_TH] = nq;
+      if (lane < nrows) {
+        hd->row_gs[lane] = gs;
+        hd->row_off[lane] = gincl - gn;
+        hd->row_ioff[lane] = iincl - galn;
+      }
+      if (lane == 0) {
+        hd->nq = nq;
+        hd->fits = fits ? 1 : 0;
+        hd->nrows = nrows;
+        hd->ylo = ylo;
+        hd->xal = xal;
+        hd->tx0 = tx0;
+        hd->ty0 = ty0;
+        hd->tx1 = tx1;
+        hd->ty1 = ty1;
+      }
+      __syncwarp();
+      if (nq == 0 || !fits) {
+        if (lane == 0) mbar_arrive(&full[s]);  // header only
+        continue;
+      }
+      if (lane == 0) {
+        uint32_t bytes = (uint32_t)npts * 16u + (uint32_t)nq * 16u + (uint32_t)nrows * (ST_CSW * 4u) +
+                         (uint32_t)nidx * 4u + (uint32_t)nqp * 4u;
+        mbar_expect_tx(&full[s], bytes);
+      }
+      __syncwarp();
+      double2* spts = reinterpret_cast<double2*>(st + L.off_pts);
+      int* scs = reinterpret_cast<int*>(st + L.off_cs);
+      double2* sq = reinterpret_cast<double2*>(st + L.off_q);
+      if (lane < nrows) {
+        if (gn > 0) bulk_g2s(spts + (gincl - gn), g.spts + (long long)gs * 2, (uint32_t)gn * 16u, &full[s]);
+        bulk_g2s(scs + lane * ST_CSW, g.cell_start + (long long)(ylo + lane) * W + xal, ST_CSW * 4u, &full[s]);
+      }
+      if (lane < ST_TH && qn > 0) bulk_g2s(sq + (qincl - qn), qs + (long long)qb * 2, (uint32_t)qn * 16u, &full[s]);
+      int* ssidx = reinterpret_cast<int*>(st + L.off_sidx);
+      int* sqperm = reinterpret_cast<int*>(st + L.off_qperm);
+      if (lane < nrows && galn > 0) bulk_g2s(ssidx + (iincl - galn), g.sidx + gal, (uint32_t)galn * 4u, &full[s]);
+      if (lane < ST_TH && qaln > 0) bulk_g2s(sqperm + (pincl - qaln), qperm + qal, (uint32_t)qaln * 4u, &full[s]);
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  // A pool of warps flows through the stages: the 32-query chunks of tile `it` are dealt to warps
+  // (rot + chunk) % NC with a rotating offset, so consecutive tiles occupy different warps and
+  // several stages are searched concurrently while others are still loading.
+  const int cw = warp - ST_PROD_WARPS;
+  constexpr int NC = ST_CONS_WARPS;
+  // A pool of warps flows through the stages IN LOCKSTEP ORDER (every warp waits on every tile's
+  // `full` and arrives on its `empty`, so no warp can run a whole ring ahead of the barrier phases);
+  // the 32-query chunks of a tile are dealt to warps (rot + chunk) % NC with a rotating offset, so
+  // consecutive tiles keep different warps busy.  With points, cell_start, queries, sidx and qperm all
+  // staged, a chunk is ~1 us of shared-memory work, short against the ring's refill latency.
+  int it = 0, rot = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    const int s = it % ST_STAGES;
+    mbar_wait(&full[s], (it / ST_STAGES) & 1);
+    unsigned char* st = stages + (size_t)s * L.stage_bytes;
+    const StreamHeader* hd = reinterpret_cast<const StreamHeader*>(st + L.off_hdr);
+    const int nq = hd->nq;
+    const int nchunk = (nq + 31) >> 5;
+    const int first = ((cw - rot) % NC + NC) % NC;  // my first chunk of this tile
+    rot = (rot + nchunk) % NC;
+    if (first < nchunk)
+    {
+      const bool fits = hd->fits != 0;
+      const double2* spts = reinterpret_cast<const double2*>(st + L.off_pts);
+      const int* scs = reinterpret_cast<const int*>(st + L.off_cs);
+      const double2* sq = reinterpret_cast<const double2*>(st + L.off_q);
+      const int* ssidx = reinterpret_cast<const int*>(st + L.off_sidx);
+      const int* sqperm = reinterpret_cast<const int*>(st + L.off_qperm);
+      const int ylo = hd->ylo, xal = hd->xal;
+      for (int t = first * 32 + lane; t < nq; t += NC * 32) {
+        int r = 0;
+#pragma unroll
+        for (int j = 1; j < ST_TH; j++)
+          if (t >= hd->qpre[j]) r = j;
+        const int spos = hd->qbeg[r] + (t - hd->qpre[r]);
+        const long long qi = fits ? (long long)sqperm[hd->qp_off[r] + (spos - (hd->qbeg[r] & ~3))]
+                                  : (long long)__ldg(qperm + spos);
+        if (!fits) {
+          int o = atomicAdd(ovf_count, 1);
+          ovf_list[o] = (int)qi;
+          continue;
+        }
+        const double2 qv = sq[t];
+        double qq[2] = {qv.x, qv.y};
+        const int cx = grid_cell(g, 0, qq[0]), cy = grid_cell(g, 1, qq[1]);
+        typename BestList<K, StageResolver>::type top;
+        top.init(StageResolver{ssidx});
+        const int bx0 = max(cx - R, 0), bx1 = min(cx + R, W - 1);
+        for (int rr = 0; rr <= 2 * R; rr++) {
+          int y = cy + ((rr & 1) ? -((rr + 1) >> 1) : (rr >> 1));  // centre row first
+          if (y < 0 || y >= H) continue;
+          const int hr = y - ylo;
+          const int s0 = scs[hr * ST_CSW + (bx0 - xal)], e0 = scs[hr * ST_CSW + (bx1 + 1 - xal)];
+          const int gs0 = hd->row_gs[hr];
+          const int base = hd->row_off[hr] - gs0;
+          const int ibase = hd->row_ioff[hr] - (gs0 & ~3);
+          for (int pos = s0; pos < e0; pos++) {
+            if (skip && skip[ssidx[ibase + pos]]) continue;
+            const double2 pv = spts[base + pos];
+            double dx = pv.x - qq[0], dy = pv.y - qq[1];
+            double sqd = 0.0;
+            sqd = sqd + dx * dx;
+            sqd = sqd + dy * dy;
+            top.offer_sq(sqd, ibase + pos);
+          }
+        }
+        for (long long i = g.n_indexed; i < n; i++) {  // unindexed tail, straight from global memory
+          if (skip && skip[i]) continue;
+          double p2[2];
+          load_point<2>(pts, i, p2);
+          top.offer_sq(sqdist<2>(p2, qq), (int)i | 0x40000000);
+        }
+        double margin = POMP_INF;
+        {
+          int lo_c = cx - R, hi_c = cx + R;
+          if (lo_c > 0) margin = fmin(margin, qq[0] - ((g.lo[0] + (double)lo_c * g.h[0]) + g.slack[0]));
+          if (hi_c < W - 1) margin = fmin(margin, ((g.lo[0] + (double)(hi_c + 1) * g.h[0]) - g.slack[0]) - qq[0]);
+          lo_c = cy - R;
+          hi_c = cy + R;
+          if (lo_c > 0) margin = fmin(margin, qq[1] - ((g.lo[1] + (double)lo_c * g.h[1]) + g.slack[1]));
+          if (hi_c < H - 1) margin = fmin(margin, ((g.lo[1] + (double)(hi_c + 1) * g.h[1]) - g.slack[1]) - qq[1]);
+        }
+        const bool exact = !(margin < POMP_INF) || (top.T * (1.0 + 1e-9) < margin);
+        if (!exact) {
+          int o = atomicAdd(ovf_count, 1);
+          ovf_list[o] = (int)qi;
+          continue;
+        }
+        int idx[K];
+        top.finish(idx);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++)
+          if (j < k) {
+            bool fin = top.d[j] < POMP_INF;
+            out_idx[qi * k + j] = fin ? (int64_t)idx[j] : -1;
+            out_dist[qi * k + j] = top.d[j];
+            cnt += fin;
+          }
+        if (out_cnt) out_cnt[qi] = cnt;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+}
+
 }  // namespace pomp

@@ -677,6 +677,7 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   for (int a = 0; a < G; a++) {
     long long nc = (long long)floor(wext[a] / cell + 0.5);
     nc = std::max<long long>(1, std::min<long long>(nc, 1 << 20));
+    if (a == 0 && G == 2 && nc >= 64) nc = (nc + 3) / 4 * 4;  // 16-byte aligned cell_start slices for the TMA path
     g.ncell[a] = (int)nc;
     total *= nc;
   }
@@ -700,7 +701,7 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   g.n_cells = total;
   g.n_indexed = (int)n;
   // counting sort of the points by cell id
-  POMP_TRY(h->cell_start.reserve((size_t)total + 1));
+  POMP_TRY(h->cell_start.reserve((size_t)total + 1 + 512));  // slack: the TMA path copies fixed-width slices
   POMP_TRY(h->tmp_i32.reserve((size_t)n + (size_t)total));
   POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(total)));
   POMP_TRY(h->spts.reserve((size_t)n * D));
@@ -836,11 +837,11 @@ static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx
   const double* qsorted = nullptr;
   const int* qstart = nullptr;
   const bool fast = is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32;
-  const bool tile = fast && h->D == 2 && h->tile_search != 0;
+  const bool tile = fast && h->D == 2 && (h->tile_search != 0 || h->stream_search != 0);
   int shift = 0, nbx = h->grid.ncell[0];
   bool ovf_zeroed = false;
   if (h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff) {
-    if (h->grid.ncell[0] >= 128) shift = (int)h->sort_shift;  // 2^shift-cell bins along axis 0 (6 = the tile kernel's TW)
+    if (h->grid.ncell[0] >= 256) shift = (fast && h->D == 2 && h->stream_search != 0) ? 6 : (int)h->sort_shift;  // 2^shift-cell bins along axis 0 (6 = the tile kernel's TW)
     nbx = (h->grid.ncell[0] + (1 << shift) - 1) >> shift;
     long long nb = (h->grid.n_cells / h->grid.ncell[0]) * nbx;
     POMP_TRY(h->counts.reserve((size_t)nb + 1 + (size_t)nb + 1));
@@ -872,7 +873,11 @@ static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx
       double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
       int R = 1;
       while (R < 6 && ppc * 3.141592653589793 * R * R < 2.5 * KK + 3.0) R++;
-      if (R <= 3 && shift == 6) {  // 3 = TILE_RMAX (grid_tile.cuh)
+      if (R <= 3 && shift == 6 && h->stream_search != 0) {  // 3 = TILE_RMAX (grid_tile.cuh)
+        int rc = launch_grid_knn_stream2d(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
+        if (rc <= 0) return rc;
+      }
+      if (R <= 3 && shift == 6 && h->tile_search != 0) {
         int rc = launch_grid_knn_tile2d_64(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
         if (rc <= 0) return rc;
       }
@@ -1231,6 +1236,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "max_tail") h->max_tail = value;
   else if (s == "block_search") h->block_search = value;
   else if (s == "tile_search") h->tile_search = value;
+  else if (s == "stream_search") h->stream_search = value;
   else if (s == "sort_min_queries") h->sort_min_queries = value;
   else if (s == "sort_shift") h->sort_shift = value;
   else if (s == "pipeline_chunks") h->pipeline_chunks = value;

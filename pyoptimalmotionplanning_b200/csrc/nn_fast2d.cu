@@ -93,3 +93,45 @@ int pomp::launch_grid_knn_tile2d_64(pomp_nn* h, const double* q, int64_t nq, con
                                     int32_t* cnt, cudaStream_t st) {
   return launch_grid_knn_tile2d<64>(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
 }
+
+// persistent TMA-pipelined kernel (grid_knn_stream2d_kernel): needs the 128-cell query sort
+// (sort_shift 7), ncell[0] % 4 == 0 and a padded cell_start array (build_grid provides both)
+int pomp::launch_grid_knn_stream2d(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
+                                   const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist,
+                                   int32_t* cnt, cudaStream_t st) {
+  const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
+  double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
+  double qdens = (double)nq / (double)h->grid.n_cells;
+  int cap_pts = ((int)(1.2 * (ST_TH + 2 * R) * (ST_TW + 2 * R) * ppc) + 96 + 3) / 4 * 4;
+  int cap_q = ((int)(1.5 * ST_TH * ST_TW * qdens) + 64 + 3) / 4 * 4;
+  StreamLayout L = stream_layout(cap_pts, cap_q);
+  size_t smem = 128 + (size_t)ST_STAGES * L.stage_bytes;
+  if (smem > 220 * 1024 || (h->grid.ncell[0] & 3) != 0 || h->n_dev >= (1LL << 30) || cap_q > 4096)
+    return 1;  // caller falls back
+  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ovf.p;
+  int* ovf_list = h->ovf.p + 1;
+  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  int ctas = sm_count(h->device);
+  int oblocks = std::min((int)((nq + 127) / 128), sm_count(h->device) * 4);
+  const uint8_t* skip = h->skip_ptr();
+#define GK(KC)                                                                                                       \
+  do {                                                                                                               \
+    auto kern = grid_knn_stream2d_kernel<KC>;                                                                        \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+    LAUNCH(kern, ctas, ST_THREADS, smem, st, h->grid, h->d_pts, (long long)h->n_dev, skip, qsorted, qperm, qstart,   \
+           nbx, k, R, cap_pts, cap_q, idx, dist, cnt, ovf_list, ovf_count);                                          \
+    prof_end(h, st);                                                                                                 \
+    LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,     \
+           (long long)nq, (const int*)nullptr, k, idx, dist, cnt, (const int*)ovf_list, (const int*)ovf_count);      \
+  } while (0)
+  prof_begin(h, st);
+  if (KK == 1) GK(1);
+  else if (KK == 4) GK(4);
+  else if (KK == 8) GK(8);
+  else if (KK == 16) GK(16);
+  else GK(32);
+#undef GK
+  CHECK_LAUNCH();
+  return POMP_OK;
+}

@@ -39,6 +39,8 @@ struct pomp_nn {
   double sort_shift = 6;
   double grid_min_queries = 64;
   double max_tail = 2048;
+  double stream_search = 0; // experimental: persistent TMA-pipelined kernel (grid_tile.cuh); slower than the flat
+                            // kernel until the index gets a blocked layout (one bulk copy per tile)
   double tile_search = 0;   // 2-D Euclidean, sorted queries: streaming TMA tile kernel (grid_tile.cuh)
   double block_search = 1;  // 2-D/3-D Euclidean: fixed block of cells + certificate (0: pruned traversal)
   // scratch for queries
@@ -113,6 +115,9 @@ namespace pomp {
 // nn_fast2d.cu: 2-D Euclidean large-batch kernels (flattened block kernel, streaming tile kernel)
 int launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm, int k,
                            int R, int64_t* idx, double* dist, int32_t* cnt, cudaStream_t st);
+int launch_grid_knn_stream2d(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
+                             const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist, int32_t* cnt,
+                             cudaStream_t st);
 int launch_grid_knn_tile2d_64(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
                               const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist, int32_t* cnt,
                               cudaStream_t st);
