@@ -166,6 +166,62 @@ struct PosMaxK {
   }
 };
 
+// k >= 8: the list lives in SHARED memory (slot-major, one column per thread: conflict-free for
+// equal slots), kept sorted by plain insertion -- dynamic indexing is free there, an insertion is a
+// short shift loop instead of 2K unrolled selects, and the kernel needs ~40 registers instead of
+// ~140 (3x the occupancy).
+template <int K, class Res = IdxResolver>
+struct SmemTopK {
+  double* sd;  // sd[j * stride]
+  int* sp;
+  int stride, filled;
+  double T, tsq;
+  Res res;
+  __device__ __forceinline__ void init(Res r, unsigned char* smem, int nthreads, int tid) {
+    res = r;
+    sd = reinterpret_cast<double*>(smem) + tid;
+    sp = reinterpret_cast<int*>(smem + (size_t)K * nthreads * sizeof(double)) + tid;
+    stride = nthreads;
+    filled = 0;
+    T = POMP_INF;
+    tsq = POMP_INF;
+  }
+  __device__ __forceinline__ double threshold() const { return T; }
+  __device__ __forceinline__ double tsq_up() const { return tsq; }
+  __device__ __forceinline__ bool full() const { return filled == K; }
+  __device__ __forceinline__ bool less_slot(double cd, int cp, int j) const {
+    double dj = sd[j * stride];
+    if (cd < dj) return true;
+    if (cd == dj) return res(cp) < res(sp[j * stride]);
+    return false;
+  }
+  __device__ __forceinline__ void offer_sq(double s, int pos) {
+    if (!(s <= tsq)) return;
+    double cd = sqrt(s);
+    if (!(cd < POMP_INF)) return;
+    int j;
+    if (filled < K) {
+      j = filled++;
+    } else {
+      if (!less_slot(cd, pos, K - 1)) return;
+      j = K - 1;
+    }
+    while (j > 0 && less_slot(cd, pos, j - 1)) {
+      sd[j * stride] = sd[(j - 1) * stride];
+      sp[j * stride] = sp[(j - 1) * stride];
+      j--;
+    }
+    sd[j * stride] = cd;
+    sp[j * stride] = pos;
+    if (filled == K) {
+      T = sd[(K - 1) * stride];
+      tsq = tsq_of(T);
+    }
+  }
+  __device__ __forceinline__ double dist_at(int j) const { return j < filled ? sd[j * stride] : POMP_INF; }
+  __device__ __forceinline__ int index_at(int j) const { return res(sp[j * stride]); }
+};
+
 template <int K, class Res = IdxResolver>
 struct BestList {  // sorted insertion for tiny k, worst-tracking for the rest
   using type = typename std::conditional<(K <= 4), PosTopK<K, Res>, PosMaxK<K, Res>>::type;
@@ -442,34 +498,63 @@ __device__ __forceinline__ bool flat2d_search(const GridDev& g, const double* __
     pre[r + 1] = pre[r] + (valid ? ee - ss : 0);
   }
   const int total = pre[NR];
-  top.init(IdxResolver{g.sidx, g.n_indexed});
   const double2* __restrict__ P = reinterpret_cast<const double2*>(g.spts);
-  for (int i = 0; i < total; i += U) {
-    double2 pv[U];
-    int pp[U];
+  if (K >= 8) {
+    // The k-list update is ~1.5 K instructions when unrolled for k >= 8; keep exactly ONE copy of it
+    // in the kernel (one candidate per iteration, the unindexed tail appended to the same stream):
+    // with several inlined copies the kernel thrashes the instruction cache.
+    const double2* __restrict__ PT = reinterpret_cast<const double2*>(pts);
+    const int ntail = (int)(n - g.n_indexed);
+#pragma unroll 1
+    for (int i = 0; i < total + ntail; i++) {
+      int pos;
+      double2 pv;
+      if (i < total) {
+        pos = s[0] + i;
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      int ii = min(i + u, total - 1);
-      int pos = s[0] + ii;
-#pragma unroll
-      for (int r = 1; r < NR; r++)
-        if (ii >= pre[r]) pos = s[r] + (ii - pre[r]);
-      pp[u] = pos;
-      pv[u] = __ldg(P + pos);
+        for (int r = 1; r < NR; r++)
+          if (i >= pre[r]) pos = s[r] + (i - pre[r]);
+        if (skip && skip[__ldg(g.sidx + pos)]) continue;
+        pv = __ldg(P + pos);
+      } else {
+        pos = g.n_indexed + (i - total);
+        if (skip && skip[pos]) continue;
+        pv = __ldg(PT + pos);
+      }
+      double dx = pv.x - qq[0], dy = pv.y - qq[1];
+      double sq = 0.0;
+      sq = sq + dx * dx;
+      sq = sq + dy * dy;
+      top.offer_sq(sq, pos);
     }
+  } else {
+    for (int i = 0; i < total; i += U) {
+      double2 pv[U];
+      int pp[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (i + u < total) {
-        if (skip && skip[__ldg(g.sidx + pp[u])]) continue;
-        double dx = pv[u].x - qq[0], dy = pv[u].y - qq[1];
-        double sq = 0.0;
-        sq = sq + dx * dx;
-        sq = sq + dy * dy;
-        top.offer_sq(sq, pp[u]);
+      for (int u = 0; u < U; u++) {
+        int ii = min(i + u, total - 1);
+        int pos = s[0] + ii;
+#pragma unroll
+        for (int r = 1; r < NR; r++)
+          if (ii >= pre[r]) pos = s[r] + (ii - pre[r]);
+        pp[u] = pos;
+        pv[u] = __ldg(P + pos);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (i + u < total) {
+          if (skip && skip[__ldg(g.sidx + pp[u])]) continue;
+          double dx = pv[u].x - qq[0], dy = pv[u].y - qq[1];
+          double sq = 0.0;
+          sq = sq + dx * dx;
+          sq = sq + dy * dy;
+          top.offer_sq(sq, pp[u]);
+        }
       }
     }
+    scan_tail<2>(g, pts, n, skip, qq, top);
   }
-  scan_tail<2>(g, pts, n, skip, qq, top);
   double margin = POMP_INF;
   {
     int lo_c = cx - R, hi_c = cx + R;
@@ -529,26 +614,48 @@ grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
     qq[1] = v.y;
   }
   const int cx = grid_cell(g, 0, qq[0]), cy = grid_cell(g, 1, qq[1]);
-  typename BestList<K>::type top;
-  bool exact = flat2d_search<K, R>(g, pts, n, skip, qq, cx, cy, top);
-  if (!exact) exact = block2d_search_nested<K>(g, pts, n, skip, qq, cx, cy, R + 1, top);
-  if (!exact) {
-    int o = atomicAdd(ovf_count, 1);
-    ovf_list[o] = (int)qi;
-    return;
-  }
-  int idx[K];
-  top.finish(idx);
-  int cnt = 0;
-#pragma unroll
-  for (int j = 0; j < K; j++)
-    if (j < k) {
-      bool fin = top.d[j] < POMP_INF;
-      out_idx[qi * k + j] = fin ? (int64_t)idx[j] : -1;
-      out_dist[qi * k + j] = top.d[j];
+  if constexpr (K >= 8) {
+    extern __shared__ __align__(16) unsigned char flat_smem[];
+    SmemTopK<K> top;
+    top.init(IdxResolver{g.sidx, g.n_indexed}, flat_smem, blockDim.x, threadIdx.x);
+    bool exact = flat2d_search<K, R>(g, pts, n, skip, qq, cx, cy, top);
+    if (!exact) {
+      int o = atomicAdd(ovf_count, 1);
+      ovf_list[o] = (int)qi;
+      return;
+    }
+    int cnt = 0;
+    for (int j = 0; j < k; j++) {
+      double dj = top.dist_at(j);
+      bool fin = dj < POMP_INF;
+      out_idx[qi * k + j] = fin ? (int64_t)top.index_at(j) : -1;
+      out_dist[qi * k + j] = dj;
       cnt += fin;
     }
-  if (out_cnt) out_cnt[qi] = cnt;
+    if (out_cnt) out_cnt[qi] = cnt;
+  } else {
+    typename BestList<K>::type top;
+    top.init(IdxResolver{g.sidx, g.n_indexed});
+    bool exact = flat2d_search<K, R>(g, pts, n, skip, qq, cx, cy, top);
+    if (!exact) exact = block2d_search_nested<K>(g, pts, n, skip, qq, cx, cy, R + 1, top);
+    if (!exact) {
+      int o = atomicAdd(ovf_count, 1);
+      ovf_list[o] = (int)qi;
+      return;
+    }
+    int idx[K];
+    top.finish(idx);
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++)
+      if (j < k) {
+        bool fin = top.d[j] < POMP_INF;
+        out_idx[qi * k + j] = fin ? (int64_t)idx[j] : -1;
+        out_dist[qi * k + j] = top.d[j];
+        cnt += fin;
+      }
+    if (out_cnt) out_cnt[qi] = cnt;
+  }
 }
 
 template <int D, bool FILL>

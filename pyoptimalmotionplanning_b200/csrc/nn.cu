@@ -805,10 +805,10 @@ static int launch_grid_knn_block(pomp_nn* h, const double* q, int64_t nq, const 
   double vol = D == 2 ? 3.141592653589793 : 4.1887902047863905;
   int R = 1;
   while (R < 6 && ppc * vol * pow((double)R, D) < 2.5 * KK + 3.0) R++;
-  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
-  int* ovf_count = h->ovf.p;
-  int* ovf_list = h->ovf.p + 1;
-  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  POMP_TRY(h->ss[h->cur].ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ss[h->cur].ovf.p;
+  int* ovf_list = h->ss[h->cur].ovf.p + 1;
+  if (!h->ss[h->cur].ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
   int blocks = (int)((nq + 127) / 128);
   int oblocks = std::min(blocks, sm_count(h->device) * 4);
   const uint8_t* skip = h->skip_ptr();
@@ -831,42 +831,63 @@ static int launch_grid_knn_block(pomp_nn* h, const double* q, int64_t nq, const 
   return POMP_OK;
 }
 
-static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
-                    cudaStream_t st) {
+struct SortInfo {
   const int* qperm = nullptr;
   const double* qsorted = nullptr;
   const int* qstart = nullptr;
-  const bool fast = is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32;
+  int shift = 0, nbx = 0;
+};
+
+static bool knn_is_fast(const pomp_nn* h, int k) { return is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32; }
+
+// counting sort of one query batch by coarse home bin into scratch set S (stream st)
+static int grid_knn_sort(pomp_nn* h, SortScratch& S, const double* q, int64_t nq, int k, SortInfo* info,
+                         cudaStream_t st) {
+  const bool fast = knn_is_fast(h, k);
+  info->shift = 0;
+  info->nbx = h->grid.ncell[0];
+  S.ovf_zeroed = false;
+  if (!(h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff)) return POMP_OK;
+  int shift = 0;
+  // 2^shift-cell bins along axis 0 (6 = the experimental tile kernels' TW)
+  if (h->grid.ncell[0] >= 256) shift = (fast && h->D == 2 && h->stream_search != 0) ? 6 : (int)h->sort_shift;
+  int nbx = (h->grid.ncell[0] + (1 << shift) - 1) >> shift;
+  long long nb = (h->grid.n_cells / h->grid.ncell[0]) * nbx;
+  POMP_TRY(S.counts.reserve((size_t)nb + 1 + (size_t)nb + 1));
+  POMP_TRY(S.qcell.reserve((size_t)nq * 2));
+  POMP_TRY(S.qperm.reserve((size_t)nq));
+  POMP_TRY(S.ovf.reserve((size_t)nq + 1));
+  if (fast && h->D == 2) POMP_TRY(S.qsorted.reserve((size_t)nq * h->D));
+  POMP_TRY(S.scan_tmp.reserve(scan_scratch_elems(nb)));
+  int* counts = S.counts.p;
+  int* start = S.counts.p + nb + 1;
+  CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nb, st));
+  int blocks = (int)((nq + 255) / 256);
+  LAUNCH(query_cell_kernel, blocks, 256, 0, st, h->grid, q, (long long)nq, h->D, shift, nbx, counts, S.qcell.p,
+         S.qcell.p + nq, S.ovf.p);
+  S.ovf_zeroed = true;
+  if (nb <= 8192) LAUNCH((scan_small_kernel<int>), 1, 1024, 0, st, counts, (int)nb, start);
+  else POMP_TRY(exclusive_scan<int>(counts, nb, start, S.scan_tmp.p, st));
+  LAUNCH(query_perm_kernel, blocks, 256, 0, st, S.qcell.p, S.qcell.p + nq, start, q, (long long)nq, h->D, S.qperm.p,
+         (fast && h->D == 2) ? S.qsorted.p : (double*)nullptr);
+  CHECK_LAUNCH();
+  info->qperm = S.qperm.p;
+  info->qstart = start;
+  if (fast && h->D == 2) info->qsorted = S.qsorted.p;
+  info->shift = shift;
+  info->nbx = nbx;
+  return POMP_OK;
+}
+
+// search of one (sorted or unsorted) batch; uses the scratch set h->cur for its overflow list
+static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int64_t nq, int k, int64_t* idx,
+                           double* dist, int32_t* cnt, cudaStream_t st) {
+  const int* qperm = si.qperm;
+  const double* qsorted = si.qsorted;
+  const int* qstart = si.qstart;
+  const int shift = si.shift, nbx = si.nbx;
+  const bool fast = knn_is_fast(h, k);
   const bool tile = fast && h->D == 2 && (h->tile_search != 0 || h->stream_search != 0);
-  int shift = 0, nbx = h->grid.ncell[0];
-  bool ovf_zeroed = false;
-  if (h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff) {
-    if (h->grid.ncell[0] >= 256) shift = (fast && h->D == 2 && h->stream_search != 0) ? 6 : (int)h->sort_shift;  // 2^shift-cell bins along axis 0 (6 = the tile kernel's TW)
-    nbx = (h->grid.ncell[0] + (1 << shift) - 1) >> shift;
-    long long nb = (h->grid.n_cells / h->grid.ncell[0]) * nbx;
-    POMP_TRY(h->counts.reserve((size_t)nb + 1 + (size_t)nb + 1));
-    POMP_TRY(h->qcell.reserve((size_t)nq * 2));
-    POMP_TRY(h->qperm.reserve((size_t)nq));
-    POMP_TRY(h->ovf.reserve((size_t)nq + 1));
-    if (fast && h->D == 2) POMP_TRY(h->qsorted.reserve((size_t)nq * h->D));
-    POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(nb)));
-    int* counts = h->counts.p;
-    int* start = h->counts.p + nb + 1;
-    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nb, st));
-    int blocks = (int)((nq + 255) / 256);
-    LAUNCH(query_cell_kernel, blocks, 256, 0, st, h->grid, q, (long long)nq, h->D, shift, nbx, counts, h->qcell.p,
-           h->qcell.p + nq, h->ovf.p);
-    ovf_zeroed = true;
-    if (nb <= 8192) LAUNCH((scan_small_kernel<int>), 1, 1024, 0, st, counts, (int)nb, start);
-    else POMP_TRY(exclusive_scan<int>(counts, nb, start, h->scan_tmp.p, st));
-    LAUNCH(query_perm_kernel, blocks, 256, 0, st, h->qcell.p, h->qcell.p + nq, start, q, (long long)nq, h->D,
-           h->qperm.p, (fast && h->D == 2) ? h->qsorted.p : (double*)nullptr);
-    CHECK_LAUNCH();
-    qperm = h->qperm.p;
-    qstart = start;
-    if (fast && h->D == 2) qsorted = h->qsorted.p;
-  }
-  h->ovf_zeroed = ovf_zeroed;
   if (fast) {
     if (tile && qsorted) {
       const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
@@ -903,6 +924,46 @@ static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx
     }
   }
   return launch_grid_knn_generic(h, q, nq, qperm, k, idx, dist, cnt, st);
+}
+
+// Large batches are cut into chunks: the bucket sort of chunk c+1 runs on an auxiliary stream
+// while chunk c is searched on the caller's stream (two scratch sets, events for the hand-over),
+// so the sort's latency-bound little kernels hide behind the search kernel.
+static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
+                    cudaStream_t st) {
+  const bool sorting = h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff;
+  const int C = (int)h->overlap_chunks;
+  if (!(sorting && C > 1 && nq >= (int64_t)h->overlap_min_queries)) {
+    h->cur = 0;
+    SortInfo si;
+    POMP_TRY(grid_knn_sort(h, h->ss[0], q, nq, k, &si, st));
+    return grid_knn_search(h, si, q, nq, k, idx, dist, cnt, st);
+  }
+  if (!h->aux_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+  while ((int)h->ovl_ev.size() < 1 + 2 * C) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ovl_ev.push_back(e);
+  }
+  cudaStream_t aux = h->aux_stream;
+  CUDA_TRY(cudaEventRecord(h->ovl_ev[0], st));
+  CUDA_TRY(cudaStreamWaitEvent(aux, h->ovl_ev[0], 0));
+  int64_t per = ((nq + C - 1) / C + 127) / 128 * 128;
+  for (int c = 0; c < C; c++) {
+    int64_t b = (int64_t)c * per, e = std::min<int64_t>(nq, b + per);
+    if (b >= e) break;
+    int64_t m = e - b;
+    cudaEvent_t ev_sorted = h->ovl_ev[1 + 2 * c], ev_done = h->ovl_ev[2 + 2 * c];
+    h->cur = c & 1;
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(aux, h->ovl_ev[2 + 2 * (c - 2)], 0));  // scratch set free again
+    SortInfo si;
+    POMP_TRY(grid_knn_sort(h, h->ss[h->cur], q + b * h->D, m, k, &si, aux));
+    CUDA_TRY(cudaEventRecord(ev_sorted, aux));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_sorted, 0));
+    POMP_TRY(grid_knn_search(h, si, q + b * h->D, m, k, idx + b * k, dist + b * k, cnt ? cnt + b : nullptr, st));
+    CUDA_TRY(cudaEventRecord(ev_done, st));
+  }
+  return POMP_OK;
 }
 
 static int bf_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
@@ -1094,6 +1155,8 @@ POMP_API int pomp_nn_destroy(pomp_nn* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ovl_ev) cudaEventDestroy(e);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
   if (h->copy_out) cudaStreamDestroy(h->copy_out);
   delete h;
@@ -1240,6 +1303,8 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "sort_min_queries") h->sort_min_queries = value;
   else if (s == "sort_shift") h->sort_shift = value;
   else if (s == "pipeline_chunks") h->pipeline_chunks = value;
+  else if (s == "overlap_chunks") h->overlap_chunks = value;
+  else if (s == "overlap_min_queries") h->overlap_min_queries = value;
   else if (s == "profile") {
     h->profile = value != 0;
     h->prof_used = 0;
@@ -1266,7 +1331,11 @@ POMP_API int pomp_nn_get_stat(pomp_nn* h, const char* name, double* out) {
     *out = (s == "search_kernel_ms") ? ms : (double)(h->prof_used / 2);
   } else if (s == "overflow_queries") {
     int c = 0;
-    if (h->ovf.p) CUDA_TRY(cudaMemcpy(&c, h->ovf.p, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 2; i++) {
+      int ci = 0;
+      if (h->ss[i].ovf.p) CUDA_TRY(cudaMemcpy(&ci, h->ss[i].ovf.p, sizeof(int), cudaMemcpyDeviceToHost));
+      c += ci;
+    }
     *out = (double)c;
   } else if (s == "n_cells") *out = h->grid_valid ? (double)h->grid.n_cells : 0.0;
   else if (s == "n_indexed") *out = h->grid_valid ? (double)h->grid.n_indexed : 0.0;

@@ -14,17 +14,21 @@ using namespace pomp;
 int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm,
                                   int k, int R, int64_t* idx, double* dist, int32_t* cnt, cudaStream_t st) {
   const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
-  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
-  int* ovf_count = h->ovf.p;
-  int* ovf_list = h->ovf.p + 1;
-  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  POMP_TRY(h->ss[h->cur].ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ss[h->cur].ovf.p;
+  int* ovf_list = h->ss[h->cur].ovf.p + 1;
+  if (!h->ss[h->cur].ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
   int blocks = (int)((nq + 127) / 128);
   int oblocks = std::min(blocks, sm_count(h->device) * 4);
   const uint8_t* skip = h->skip_ptr();
 #define GKR(KC, RC)                                                                                              \
   do {                                                                                                           \
-    LAUNCH((grid_knn_flat2d_kernel<KC, RC>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, \
-           qsorted, (long long)nq, qperm, k, idx, dist, cnt, ovf_list, ovf_count);                               \
+    size_t fsm = KC >= 8 ? (size_t)KC * 128 * 12 : 0; /* SmemTopK: K x 128 threads x (8 + 4) bytes */           \
+    if (fsm > 48 * 1024)                                                                                         \
+      CUDA_TRY(cudaFuncSetAttribute(grid_knn_flat2d_kernel<KC, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)fsm));                                                                  \
+    LAUNCH((grid_knn_flat2d_kernel<KC, RC>), blocks, 128, fsm, st, h->grid, h->d_pts, (long long)h->n_dev, skip, \
+           q, qsorted, (long long)nq, qperm, k, idx, dist, cnt, ovf_list, ovf_count);                            \
     prof_end(h, st);                                                                                             \
     LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,  \
            (long long)nq, (const int*)nullptr, k, idx, dist, cnt, (const int*)ovf_list, (const int*)ovf_count);  \
@@ -58,10 +62,10 @@ static int launch_grid_knn_tile2d(pomp_nn* h, const double* q, int64_t nq, const
   int cap = (int)(1.5 * (TH + 2 * R) * (TW + 2 * R) * ppc) + 128;
   size_t smem = (size_t)cap * 16 + sizeof(TileShared<TW, TH>);
   if (smem > 200 * 1024) return 1;  // caller falls back
-  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
-  int* ovf_count = h->ovf.p;
-  int* ovf_list = h->ovf.p + 1;
-  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  POMP_TRY(h->ss[h->cur].ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ss[h->cur].ovf.p;
+  int* ovf_list = h->ss[h->cur].ovf.p + 1;
+  if (!h->ss[h->cur].ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
   const int W = h->grid.ncell[0], H = h->grid.ncell[1];
   int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
   int oblocks = std::min((int)((nq + 127) / 128), sm_count(h->device) * 4);
@@ -108,10 +112,10 @@ int pomp::launch_grid_knn_stream2d(pomp_nn* h, const double* q, int64_t nq, cons
   size_t smem = 128 + (size_t)ST_STAGES * L.stage_bytes;
   if (smem > 220 * 1024 || (h->grid.ncell[0] & 3) != 0 || h->n_dev >= (1LL << 30) || cap_q > 4096)
     return 1;  // caller falls back
-  POMP_TRY(h->ovf.reserve((size_t)nq + 1));
-  int* ovf_count = h->ovf.p;
-  int* ovf_list = h->ovf.p + 1;
-  if (!h->ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  POMP_TRY(h->ss[h->cur].ovf.reserve((size_t)nq + 1));
+  int* ovf_count = h->ss[h->cur].ovf.p;
+  int* ovf_list = h->ss[h->cur].ovf.p + 1;
+  if (!h->ss[h->cur].ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
   int ctas = sm_count(h->device);
   int oblocks = std::min((int)((nq + 127) / 128), sm_count(h->device) * 4);
   const uint8_t* skip = h->skip_ptr();

@@ -8,6 +8,14 @@
 
 using namespace pomp;
 
+// scratch of one bucket-sorted query batch (two sets: sort of chunk c+1 overlaps search of chunk c)
+struct SortScratch {
+  pomp::DevBuf<int> counts, qcell, qperm, ovf;  // ovf[0] = overflow count, ovf[1..] = overflow query ids
+  pomp::DevBuf<double> qsorted;
+  pomp::DevBuf<long long> scan_tmp;
+  bool ovf_zeroed = false;
+};
+
 // ============================================================================ handle
 struct pomp_nn {
   int device = 0;
@@ -51,8 +59,13 @@ struct pomp_nn {
   DevBuf<int> qperm;
   DevBuf<int> qcell;
   DevBuf<double> qsorted;
-  bool ovf_zeroed = false;
-  DevBuf<int> ovf;  // [0] = overflow count, [1..] = overflow query ids
+  SortScratch ss[2];
+  int cur = 0;  // scratch set of the chunk being searched
+  cudaStream_t aux_stream = nullptr;  // runs the query sort of the next chunk
+  std::vector<cudaEvent_t> ovl_ev;
+  double overlap_chunks = 1;          // chunks per large device batch; >1 overlaps sort and search on two
+                                      // streams -- measured SLOWER on B200 (host launch rate bound), kept as a knob
+  double overlap_min_queries = 524288;
   DevBuf<int64_t> out_idx;
   DevBuf<double> out_dist;
   DevBuf<int32_t> out_cnt;
