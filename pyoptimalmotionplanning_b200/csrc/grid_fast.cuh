@@ -598,21 +598,11 @@ __device__ __forceinline__ bool block2d_search_nested(const GridDev& g, const do
 // retried once in place with the next larger block (rare: ~exp(-pi*ppc*R^2) of the queries for
 // k=1); only if that fails too does it go to the overflow list for the pruned traversal.
 template <int K, int R>
-__global__ void __launch_bounds__(128)
-grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
-                       const double* __restrict__ q, const double* __restrict__ qs, long long nq,
-                       const int* __restrict__ qperm, int k, int64_t* __restrict__ out_idx,
-                       double* __restrict__ out_dist, int32_t* __restrict__ out_cnt, int* __restrict__ ovf_list,
-                       int* __restrict__ ovf_count) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nq) return;
-  long long qi = qperm ? (long long)__ldg(qperm + t) : t;
-  double qq[2];
-  {
-    double2 v = qs ? __ldg(reinterpret_cast<const double2*>(qs) + t) : __ldg(reinterpret_cast<const double2*>(q) + qi);
-    qq[0] = v.x;
-    qq[1] = v.y;
-  }
+__device__ __forceinline__ void flat2d_one(const GridDev& g, const double* __restrict__ pts, long long n,
+                                           const uint8_t* __restrict__ skip, const double (&qq)[2], long long qi,
+                                           int k, int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                           int32_t* __restrict__ out_cnt, int* __restrict__ ovf_list,
+                                           int* __restrict__ ovf_count) {
   const int cx = grid_cell(g, 0, qq[0]), cy = grid_cell(g, 1, qq[1]);
   if constexpr (K >= 8) {
     extern __shared__ __align__(16) unsigned char flat_smem[];
@@ -656,6 +646,32 @@ grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
       }
     if (out_cnt) out_cnt[qi] = cnt;
   }
+}
+
+template <int K, int R>
+__global__ void __launch_bounds__(128, (K <= 4 ? 8 : 4))
+grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                       const double* __restrict__ q, const double* __restrict__ qs, long long nq,
+                       const int* __restrict__ qperm, int k, int64_t* __restrict__ out_idx,
+                       double* __restrict__ out_dist, int32_t* __restrict__ out_cnt, int* __restrict__ ovf_list,
+                       int* __restrict__ ovf_count, const int* __restrict__ qlist, const int* __restrict__ qcount) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qlist) {
+    // second-chance pass: grid-stride over the overflow list of the smaller block
+    const long long cnt = *qcount;
+    for (; t < cnt; t += (long long)gridDim.x * blockDim.x) {
+      const long long qi = qlist[t];
+      double2 v = __ldg(reinterpret_cast<const double2*>(q) + qi);
+      double qq[2] = {v.x, v.y};
+      flat2d_one<K, R>(g, pts, n, skip, qq, qi, k, out_idx, out_dist, out_cnt, ovf_list, ovf_count);
+    }
+    return;
+  }
+  if (t >= nq) return;
+  const long long qi = qperm ? (long long)__ldg(qperm + t) : t;
+  double2 v = qs ? __ldg(reinterpret_cast<const double2*>(qs) + t) : __ldg(reinterpret_cast<const double2*>(q) + qi);
+  double qq[2] = {v.x, v.y};
+  flat2d_one<K, R>(g, pts, n, skip, qq, qi, k, out_idx, out_dist, out_cnt, ovf_list, ovf_count);
 }
 
 template <int D, bool FILL>

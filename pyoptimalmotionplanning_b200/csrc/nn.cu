@@ -908,8 +908,11 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
         if (h->block_search != 0) {
           const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
           double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
+          // expected points inside the certified ball of radius R cells: generous for tiny k (a miss
+          // costs an in-thread retry), tight for k >= 8 (misses are compacted into a second pass)
+          const double need = KK >= 8 ? 1.4 * KK + 2.0 : 2.5 * KK + 3.0;
           int R = 1;
-          while (R < 6 && ppc * 3.141592653589793 * R * R < 2.5 * KK + 3.0) R++;
+          while (R < 6 && ppc * 3.141592653589793 * R * R < need) R++;
           if (R <= 3) return launch_grid_knn_flat2d(h, q, qsorted, nq, qperm, k, R, idx, dist, cnt, st);
           return launch_grid_knn_block<2>(h, q, nq, qperm, k, idx, dist, cnt, st);
         }

@@ -12,32 +12,52 @@ using namespace pomp;
 
 // 2-D: flattened fixed-block kernel (grid_knn_flat2d_kernel) + overflow pass
 int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm,
-                                  int k, int R, int64_t* idx, double* dist, int32_t* cnt, cudaStream_t st) {
+                                 int k, int R, int64_t* idx, double* dist, int32_t* cnt, cudaStream_t st) {
   const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
-  POMP_TRY(h->ss[h->cur].ovf.reserve((size_t)nq + 1));
-  int* ovf_count = h->ss[h->cur].ovf.p;
-  int* ovf_list = h->ss[h->cur].ovf.p + 1;
-  if (!h->ss[h->cur].ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  SortScratch& S = h->ss[h->cur];
+  // two overflow lists: [0] count1, [1..nq] list1, [nq+1] count2, [nq+2..] list2
+  POMP_TRY(S.ovf.reserve(2 * (size_t)nq + 2));
+  int* c1 = S.ovf.p;
+  int* l1 = S.ovf.p + 1;
+  int* c2 = S.ovf.p + nq + 1;
+  int* l2 = S.ovf.p + nq + 2;
+  if (!S.ovf_zeroed) CUDA_TRY(cudaMemsetAsync(c1, 0, sizeof(int), st));
+  const bool two_stage = KK >= 8 && R < 3;  // k >= 8: small block first, R+1 for the few that fail
+  if (two_stage) CUDA_TRY(cudaMemsetAsync(c2, 0, sizeof(int), st));
   int blocks = (int)((nq + 127) / 128);
   int oblocks = std::min(blocks, sm_count(h->device) * 4);
   const uint8_t* skip = h->skip_ptr();
-#define GKR(KC, RC)                                                                                              \
-  do {                                                                                                           \
-    size_t fsm = KC >= 8 ? (size_t)KC * 128 * 12 : 0; /* SmemTopK: K x 128 threads x (8 + 4) bytes */           \
-    if (fsm > 48 * 1024)                                                                                         \
-      CUDA_TRY(cudaFuncSetAttribute(grid_knn_flat2d_kernel<KC, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)fsm));                                                                  \
-    LAUNCH((grid_knn_flat2d_kernel<KC, RC>), blocks, 128, fsm, st, h->grid, h->d_pts, (long long)h->n_dev, skip, \
-           q, qsorted, (long long)nq, qperm, k, idx, dist, cnt, ovf_list, ovf_count);                            \
-    prof_end(h, st);                                                                                             \
-    LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,  \
-           (long long)nq, (const int*)nullptr, k, idx, dist, cnt, (const int*)ovf_list, (const int*)ovf_count);  \
+  const int* np = nullptr;
+  const double* npd = nullptr;
+#define FLAT(KC, RC, NB, QS, QP, OL, OC, QL, QC)                                                                   \
+  do {                                                                                                             \
+    size_t fsm = KC >= 8 ? (size_t)KC * 128 * 12 : 0; /* SmemTopK: K x 128 threads x (8 + 4) bytes */             \
+    if (fsm > 48 * 1024)                                                                                           \
+      CUDA_TRY(cudaFuncSetAttribute(grid_knn_flat2d_kernel<KC, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                    (int)fsm));                                                                    \
+    LAUNCH((grid_knn_flat2d_kernel<KC, RC>), NB, 128, fsm, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, QS, \
+           (long long)nq, QP, k, idx, dist, cnt, OL, OC, QL, QC);                                                  \
   } while (0)
-#define GK(KC)                 \
-  do {                         \
-    if (R == 1) GKR(KC, 1);    \
+#define PRUNED(KC, OL, OC)                                                                                         \
+  LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,     \
+         (long long)nq, np, k, idx, dist, cnt, (const int*)OL, (const int*)OC)
+#define GKR(KC, RC)                                                                                                \
+  do {                                                                                                             \
+    FLAT(KC, RC, blocks, qsorted, qperm, l1, c1, np, np);                                                          \
+    prof_end(h, st);                                                                                               \
+    if (two_stage) {                                                                                               \
+      /* list length is unknown on the host: launch enough blocks for 1/8 of the batch, rest -> pruned */        \
+      FLAT(KC, (RC < 3 ? RC + 1 : 3), (blocks + 7) / 8, npd, np, l2, c2, (const int*)l1, (const int*)c1);          \
+      PRUNED(KC, l2, c2);                                                                                          \
+    } else {                                                                                                       \
+      PRUNED(KC, l1, c1);                                                                                          \
+    }                                                                                                              \
+  } while (0)
+#define GK(KC)                   \
+  do {                           \
+    if (R == 1) GKR(KC, 1);      \
     else if (R == 2) GKR(KC, 2); \
-    else GKR(KC, 3);           \
+    else GKR(KC, 3);             \
   } while (0)
   prof_begin(h, st);
   if (KK == 1) GK(1);
@@ -47,6 +67,8 @@ int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsor
   else GK(32);
 #undef GK
 #undef GKR
+#undef PRUNED
+#undef FLAT
   CHECK_LAUNCH();
   return POMP_OK;
 }
