@@ -272,6 +272,16 @@ def run_extras(peak):
         iters += 10
     dt = time.perf_counter() - t0
     out["rrrt_bugtrap"] = {"iters_per_s": iters / dt, "best_cost": p.bestPathCost}
+    # the same planner as 10 (main.py's numTrials) and 64 seeded trials in lock step: one launch per iteration
+    from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest
+    for T, its in ((10, 4000), (64, 1500)):
+        rf = RepeatedRRTForest(bug, [0.1, 0.5], list(range(T)), [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01)
+        rf.planMore(50)
+        t0 = time.perf_counter()
+        rf.planMore(its)
+        dt = time.perf_counter() - t0
+        out["rrrt_bugtrap_lockstep_%dtrials" % T] = {"iters_per_s": T * its / dt, "per_trial_iters_per_s": its / dt,
+                                                    "best_cost_trial0": rf.bestPathCost[0]}
     return out
 
 

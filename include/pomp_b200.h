@@ -262,6 +262,22 @@ int pomp_rrt_extend_h(pomp_nn* h, pomp_space* s, const double* xrand_h, int chec
                       double resolution, int64_t* parent_h, double* xnew_h, double* edge_len_h,
                       int32_t* added_h);
 
+/* ---------------------------------------------------------------- lock-step trials ------ */
+/* T independent kinematic RRTs (main.py runs 10 trials per configuration, pomp/planners/test.py:8-52;
+   BASELINE config 5 asks for thousands) advanced by one RRT.expand EACH in one launch: one block per
+   trial over a device arena [T][capacity][dim].  Per trial the semantics are exactly those of
+   pomp_rrt_extend_h; reset_h[t] != 0 restarts trial t from root_h first (RRT.reset,
+   kinodynamicplanner.py:312-320); active_h[t] == 0 skips it (parent -3).  The host keeps one RNG per
+   trial, so every tree equals the single-trial one.  POMP_ERR_CAPACITY if a tree is full. */
+typedef struct pomp_forest pomp_forest;
+int pomp_forest_create(int dim, int n_trials, int64_t capacity_per_trial, int device, pomp_forest** out);
+int pomp_forest_destroy(pomp_forest* f);
+int64_t pomp_forest_size(const pomp_forest* f, int trial);
+int pomp_forest_extend_h(pomp_forest* f, pomp_space* s, const double* xrand_h, const double* root_h,
+                         const uint8_t* active_h, const uint8_t* reset_h, int check_sample, double max_step,
+                         double resolution, int64_t* parent_h, double* xnew_h, double* edge_len_h,
+                         int32_t* added_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,10 @@ SIGNATURES = {
     "pomp_next_state_h": (C.c_int, [_DD, _P, _P, _I64, _P]),
     "pomp_select_control": (C.c_int, [_DD, _MD, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P]),
     "pomp_select_control_h": (C.c_int, [_DD, _MD, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "pomp_forest_create": (C.c_int, [C.c_int, C.c_int, _I64, C.c_int, C.POINTER(_P)]),
+    "pomp_forest_destroy": (C.c_int, [_P]),
+    "pomp_forest_size": (_I64, [_P, C.c_int]),
+    "pomp_forest_extend_h": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _D, _D, _P, _P, _P, _P]),
     "pomp_rrt_extend_h": (C.c_int, [_P, _P, _P, C.c_int, _D, _D, _P, _P, _P, _P]),
 }
 

@@ -318,6 +318,48 @@ def rrt_extend(nn, space, xrand, max_step, resolution, check_sample=True, _buf={
     return parent.value, list(xn), elen.value, bool(added.value)
 
 
+class CudaForest(object):
+    """T independent kinematic RRTs advanced in lock step, one launch per iteration
+    (pomp_forest_* entry points)."""
+
+    def __init__(self, dim, n_trials, capacity=16384, device=0):
+        self.lib = _abi.load_library()
+        self.dim, self.T = dim, n_trials
+        self._h = C.c_void_p()
+        check(self.lib, self.lib.pomp_forest_create(dim, n_trials, capacity, device, C.byref(self._h)))
+        T, D = n_trials, dim
+        self.xrand = (C.c_double * (T * D))()
+        self.root = (C.c_double * D)()
+        self.active = (C.c_uint8 * T)()
+        self.reset = (C.c_uint8 * T)()
+        self.parent = (C.c_int64 * T)()
+        self.xnew = (C.c_double * (T * D))()
+        self.elen = (C.c_double * T)()
+        self.added = (C.c_int32 * T)()
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self.lib.pomp_forest_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self, trial):
+        return self.lib.pomp_forest_size(self._h, trial)
+
+    def extend(self, space, max_step, resolution, check_sample=True):
+        """Inputs are read from self.xrand / self.root / self.active / self.reset, results land in
+        self.parent / self.xnew / self.elen / self.added."""
+        check(self.lib, self.lib.pomp_forest_extend_h(self._h, space._h, self.xrand, self.root, self.active,
+                                                      self.reset, 1 if check_sample else 0, float(max_step),
+                                                      float(resolution), self.parent, self.xnew, self.elen,
+                                                      self.added))
+
+
 def launch_count():
     return _abi.load_library().pomp_launch_count()
 

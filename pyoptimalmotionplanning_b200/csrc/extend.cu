@@ -187,3 +187,263 @@ POMP_API int pomp_rrt_extend_h(pomp_nn* h, pomp_space* sp, const double* xrand_h
   if (mb->aux[0]) h->n_dev += 1;
   return POMP_OK;
 }
+
+// ============================================================================ forest: lock-step trials
+// T independent kinematic RRTs advanced by one RRT.expand each in ONE launch (one block per
+// trial).  The planner loop is latency bound (one launch + one sync per iteration, tiny trees);
+// running independent seeded trials in lock step -- main.py runs 10 per configuration,
+// BASELINE config 5 asks for 4096 -- amortises that latency over all of them.  Every trial keeps
+// its own host RNG, so each tree is identical to the one the single-trial driver grows.
+struct pomp_forest {
+  int device = 0, D = 0, T = 0;
+  int64_t cap = 0;
+  double* d_pts = nullptr;  // [T][cap][D]
+  int* d_count = nullptr;   // [T] nodes per trial (device-side truth; host mirror in h_count)
+  std::vector<int64_t> h_count;
+  // zero-copy mailboxes (mapped pinned memory)
+  struct In {
+    double xrand[POMP_MAX_DIM];
+    double root[POMP_MAX_DIM];
+    int32_t active, reset;
+  };
+  struct Out {
+    int64_t parent;
+    double xnew[POMP_MAX_DIM];
+    double len;
+    int32_t added, overflow;
+  };
+  In* in_h = nullptr;
+  In* in_d = nullptr;
+  Out* out_h = nullptr;
+  Out* out_d = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+__global__ void __launch_bounds__(256)
+forest_extend_kernel(double* __restrict__ pts, int* __restrict__ count, long long cap, int D, SpaceDev s,
+                     const pomp_forest::In* __restrict__ in, pomp_forest::Out* __restrict__ out, int check_sample,
+                     double max_step, double res) {
+  const int t = blockIdx.x;
+  __shared__ pomp_forest::In job;
+  __shared__ int n_sh, sample_ok;
+  if (threadIdx.x == 0) {
+    job = in[t];  // one read of the mapped host record
+    int n = count[t];
+    if (job.reset) {  // RRT.reset (:312-320): the tree restarts from its root
+      for (int j = 0; j < D; j++) pts[(long long)t * cap * D + j] = job.root[j];
+      n = 1;
+      count[t] = 1;
+    }
+    n_sh = n;
+    sample_ok = (!check_sample || feasible_pt(s, job.xrand)) ? 1 : 0;
+  }
+  __syncthreads();
+  pomp_forest::Out* o = out + t;
+  if (!job.active) return;
+  const int n = n_sh;
+  double* P = pts + (long long)t * cap * D;
+  if (!sample_ok || n >= cap) {
+    if (threadIdx.x == 0) {
+      o->parent = sample_ok ? -1 : -2;
+      o->added = 0;
+      o->overflow = (sample_ok && n >= cap) ? 1 : 0;
+      o->len = 0.0;
+      __threadfence_system();
+    }
+    return;
+  }
+  // nearest node of this trial's tree (strict '<' in index order: nearestneighbors.py:88-96)
+  double bd = POMP_INF;
+  int bi = IDX_NONE;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double sm = 0.0;
+    for (int j = 0; j < D; j++) {
+      double tt = P[(long long)i * D + j] - job.xrand[j];
+      sm = sm + tt * tt;
+    }
+    double d = sqrt(sm);
+    if (key_less(d, i, bd, bi)) {
+      bd = d;
+      bi = i;
+    }
+  }
+  __shared__ double sd[8];
+  __shared__ int si[8];
+  __shared__ double xn[POMP_MAX_DIM], xnew[POMP_MAX_DIM];
+  __shared__ long long ks;
+  __shared__ double elen;
+  __shared__ int parent;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double od = __shfl_xor_sync(FULL_MASK, bd, off);
+    int oi = __shfl_xor_sync(FULL_MASK, bi, off);
+    if (key_less(od, oi, bd, bi)) {
+      bd = od;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    sd[w] = bd;
+    si[w] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int x = 1; x < nw; x++)
+      if (key_less(sd[x], si[x], bd, bi)) {
+        bd = sd[x];
+        bi = si[x];
+      }
+    bool found = bd < POMP_INF;
+    parent = found ? bi : -1;
+    ks = -1;
+    elen = 0.0;
+    if (found) {
+      double sm = 0.0;
+      for (int j = 0; j < D; j++) {
+        xn[j] = P[(long long)bi * D + j];
+        double tt = xn[j] - job.xrand[j];
+        sm = sm + tt * tt;
+      }
+      double d = sqrt(sm);
+      if (d > max_step) {
+        double u = max_step / d;
+        for (int j = 0; j < D; j++) xnew[j] = xn[j] + u * (job.xrand[j] - xn[j]);
+      } else {
+        for (int j = 0; j < D; j++) xnew[j] = job.xrand[j];
+      }
+      double l = 0.0;
+      for (int j = 0; j < D; j++) {
+        double tt = xn[j] - xnew[j];
+        l = l + tt * tt;
+      }
+      elen = sqrt(l);
+      ks = edge_samples(elen, res);
+    }
+  }
+  __syncthreads();
+  int ok = 1;
+  if (parent < 0) {
+    ok = 0;
+  } else {
+    const long long total = ks + 2;
+    const double kk2 = (double)(ks + 2);
+    for (long long q = threadIdx.x; q < total && ok; q += blockDim.x) {
+      double x[POMP_MAX_DIM];
+      if (q == 0) {
+        for (int j = 0; j < D; j++) x[j] = xn[j];
+      } else if (q == 1) {
+        for (int j = 0; j < D; j++) x[j] = xnew[j];
+      } else {
+        double u = (double)(q - 1) / kk2;
+        for (int j = 0; j < D; j++) x[j] = xn[j] + u * (xnew[j] - xn[j]);
+      }
+      if (!feasible_pt(s, x)) ok = 0;
+    }
+  }
+  ok = __syncthreads_and(ok);
+  if (threadIdx.x == 0) {
+    o->parent = parent;
+    o->added = ok;
+    o->overflow = 0;
+    o->len = elen;
+    for (int j = 0; j < D; j++) o->xnew[j] = parent >= 0 ? xnew[j] : nan("");
+    if (ok) {
+      for (int j = 0; j < D; j++) P[(long long)n * D + j] = xnew[j];
+      count[t] = n + 1;
+    }
+    __threadfence_system();
+  }
+}
+
+POMP_API int pomp_forest_create(int dim, int n_trials, int64_t capacity_per_trial, int device, pomp_forest** out) {
+  POMP_REQUIRE(out, "out is NULL");
+  *out = nullptr;
+  POMP_REQUIRE(dim >= 1 && dim <= POMP_MAX_DIM && n_trials >= 1 && capacity_per_trial >= 2, "bad forest shape");
+  DeviceGuard g(device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  pomp_forest* f = new pomp_forest();
+  f->device = device;
+  f->D = dim;
+  f->T = n_trials;
+  f->cap = capacity_per_trial;
+  f->h_count.assign((size_t)n_trials, 0);
+  cudaError_t e = cudaMalloc((void**)&f->d_pts, sizeof(double) * (size_t)n_trials * capacity_per_trial * dim);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_count, sizeof(int) * (size_t)n_trials);
+  if (e == cudaSuccess) e = cudaMemset(f->d_count, 0, sizeof(int) * (size_t)n_trials);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->in_h, sizeof(pomp_forest::In) * (size_t)n_trials, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->out_h, sizeof(pomp_forest::Out) * (size_t)n_trials, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&f->in_d, f->in_h, 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&f->out_d, f->out_h, 0);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("pomp_forest_create: %s", cudaGetErrorString(e));
+    pomp_forest_destroy(f);
+    return e == cudaErrorMemoryAllocation ? POMP_ERR_NOMEM : POMP_ERR_CUDA;
+  }
+  memset(f->in_h, 0, sizeof(pomp_forest::In) * (size_t)n_trials);
+  *out = f;
+  return POMP_OK;
+}
+
+POMP_API int pomp_forest_destroy(pomp_forest* f) {
+  if (!f) return POMP_OK;
+  DeviceGuard g(f->device);
+  if (f->d_pts) cudaFree(f->d_pts);
+  if (f->d_count) cudaFree(f->d_count);
+  if (f->in_h) cudaFreeHost(f->in_h);
+  if (f->out_h) cudaFreeHost(f->out_h);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+  return POMP_OK;
+}
+
+POMP_API int64_t pomp_forest_size(const pomp_forest* f, int trial) {
+  return (f && trial >= 0 && trial < f->T) ? f->h_count[(size_t)trial] : -1;
+}
+
+POMP_API int pomp_forest_extend_h(pomp_forest* f, pomp_space* sp, const double* xrand_h, const double* root_h,
+                                  const uint8_t* active_h, const uint8_t* reset_h, int check_sample, double max_step,
+                                  double resolution, int64_t* parent_h, double* xnew_h, double* edge_len_h,
+                                  int32_t* added_h) {
+  POMP_REQUIRE(f && sp && xrand_h && root_h && parent_h && xnew_h && added_h, "NULL argument to pomp_forest_extend_h");
+  POMP_REQUIRE(sp->dev.dim == f->D && sp->device == f->device, "space does not match the forest");
+  POMP_REQUIRE(resolution > 0.0 && max_step >= 0.0, "bad step/resolution");
+  DeviceGuard g(f->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  const int D = f->D, T = f->T;
+  for (int t = 0; t < T; t++) {
+    pomp_forest::In& in = f->in_h[t];
+    for (int j = 0; j < D; j++) {
+      in.xrand[j] = xrand_h[(size_t)t * D + j];
+      in.root[j] = root_h[j];
+    }
+    in.active = active_h ? (active_h[t] != 0) : 1;
+    in.reset = (reset_h ? (reset_h[t] != 0) : 0) || f->h_count[(size_t)t] == 0;
+    if (in.reset) f->h_count[(size_t)t] = 1;
+  }
+  LAUNCH(forest_extend_kernel, T, 256, 0, f->stream, f->d_pts, f->d_count, (long long)f->cap, D, sp->dev, f->in_d,
+         f->out_d, check_sample, max_step, resolution);
+  CHECK_LAUNCH();
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  int overflow = 0;
+  for (int t = 0; t < T; t++) {
+    if (active_h && !active_h[t]) {
+      parent_h[t] = -3;
+      added_h[t] = 0;
+      continue;
+    }
+    const pomp_forest::Out& o = f->out_h[t];
+    parent_h[t] = o.parent;
+    added_h[t] = o.added;
+    if (edge_len_h) edge_len_h[t] = o.len;
+    for (int j = 0; j < D; j++) xnew_h[(size_t)t * D + j] = o.xnew[j];
+    if (o.added) f->h_count[(size_t)t] += 1;
+    overflow |= o.overflow;
+  }
+  if (overflow) {
+    set_error("a trial's tree reached the forest capacity of %lld nodes", (long long)f->cap);
+    return POMP_ERR_CAPACITY;
+  }
+  return POMP_OK;
+}

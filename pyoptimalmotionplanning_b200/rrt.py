@@ -146,3 +146,127 @@ class RepeatedRRT(RRT):
                 RRT.reset(self)  # numIters restarts too, as in the reference (:319,1307)
                 return improved
         return False
+
+
+class RRTForest(object):
+    """T independent RRT trials advanced in LOCK STEP: one fused launch per iteration serves all of
+    them (`pomp_forest_extend_h`).  Trial t draws from its own `random.Random(seeds[t])`, in the
+    reference's order, so its tree is exactly the tree the single-trial planner grows under
+    `random.seed(seeds[t])` (pomp/planners/test.py runs such trials one after the other)."""
+
+    def __init__(self, space, start, seeds, goal=None, goal_radius=None, max_step=0.1, resolution=0.01,
+                 p_choose_goal=0.1, capacity=16384, device=0, _backends=None):
+        self.spec = space_from_pomp(space)
+        self.D = self.spec.dim
+        self.T = len(seeds)
+        self.start = list(start)
+        self.goal = None if goal is None else list(goal)
+        self.goal_radius = goal_radius
+        self.max_step = max_step
+        self.resolution = resolution
+        self.pChooseGoal = p_choose_goal
+        if _backends is None:
+            from .backend import CudaForest, CudaSpace
+            _backends = (CudaForest, CudaSpace)
+        forest_cls, space_cls = _backends
+        self._forest = forest_cls(self.D, self.T, capacity, device)
+        self._space = space_cls(self.spec, device)
+        self.rngs = [random.Random(s) for s in seeds]
+        for j in range(self.D):
+            self._forest.root[j] = self.start[j]
+        self.nodes = [[self.start] for _ in range(self.T)]
+        self.parents = [[-1] for _ in range(self.T)]
+        self.costs = [[0.0] for _ in range(self.T)]
+        self.numIters = [0] * self.T
+        self._pending_reset = [True] * self.T
+        self._lo_hi = list(zip(self.spec.lo, self.spec.hi))
+
+    def reset_trial(self, t):
+        self.nodes[t] = [self.start]
+        self.parents[t] = [-1]
+        self.costs[t] = [0.0]
+        self.numIters[t] = 0
+        self._pending_reset[t] = True
+
+    def expand_all(self, active=None):
+        """One RRT.expand per active trial; returns the list of new node indices (None where no node
+        was added or the trial is inactive)."""
+        f, D = self._forest, self.D
+        xr = f.xrand
+        goal, r, p = self.goal, self.goal_radius, self.pChooseGoal
+        for t in range(self.T):
+            on = active is None or active[t]
+            f.active[t] = 1 if on else 0
+            f.reset[t] = 1 if self._pending_reset[t] else 0
+            if not on:
+                continue
+            self._pending_reset[t] = False
+            rng = self.rngs[t]
+            b = t * D
+            if goal is not None and rng.uniform(0.0, 1.0) < p:
+                for j in range(D):
+                    xr[b + j] = goal[j] + rng.uniform(-r, r)
+            else:
+                for j, (lo, hi) in enumerate(self._lo_hi):
+                    xr[b + j] = rng.uniform(lo, hi)
+        f.extend(self._space, self.max_step, self.resolution, True)
+        out = [None] * self.T
+        added, parent, xnew, elen = f.added, f.parent, f.xnew, f.elen
+        for t in range(self.T):
+            if f.active[t] and added[t]:
+                b = t * D
+                par = parent[t]
+                self.nodes[t].append([xnew[b + j] for j in range(D)])
+                self.parents[t].append(par)
+                self.costs[t].append(self.costs[t][par] + elen[t])
+                out[t] = len(self.nodes[t]) - 1
+        return out
+
+    def goal_contains(self, x):
+        s = 0
+        for a, b in zip(x, self.goal):
+            s = s + (a - b) * (a - b)
+        return math.sqrt(s) <= self.goal_radius
+
+    def planMore(self, iters):
+        for _ in range(iters):
+            for t in range(self.T):
+                self.numIters[t] += 1
+            self.expand_all()
+
+    def trial(self, t):
+        """A read-only single-trial view (nodes / parents / getRoadmap / roadmap_hash) of trial t."""
+        v = RRT.__new__(RRT)
+        v.nodes, v.parents, v.costs = self.nodes[t], self.parents[t], self.costs[t]
+        return v
+
+
+class RepeatedRRTForest(RRTForest):
+    """'r-rrt' trials in lock step: per trial, keep the best path cost and restart the tree at every
+    goal hit (RepeatedRRT.planMore, kinodynamicplanner.py:1291-1312)."""
+
+    def __init__(self, *args, **kwargs):
+        RRTForest.__init__(self, *args, **kwargs)
+        self.bestPathCost = [None] * self.T
+        self.bestPath = [None] * self.T
+        self.totalIters = [0] * self.T
+
+    def planMore(self, iters):
+        for _ in range(iters):
+            new = self.expand_all()
+            for t, n in enumerate(new):
+                self.numIters[t] += 1
+                self.totalIters[t] += 1
+                if n is None:
+                    continue
+                if self.goal is not None and self.goal_contains(self.nodes[t][n]):
+                    totalcost = self.costs[t][n] + 0
+                    if self.bestPath[t] is None or totalcost < self.bestPathCost[t]:
+                        self.bestPathCost[t] = totalcost
+                        path, i = [], n
+                        while i >= 0:
+                            path.append(self.nodes[t][i])
+                            i = self.parents[t][i]
+                        path.reverse()
+                        self.bestPath[t] = path
+                    self.reset_trial(t)

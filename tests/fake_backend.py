@@ -127,3 +127,34 @@ def oracle_rrt_extend(nn, space, xrand, max_step, res, check_sample=True):
     if added:
         nn.add([xnew])
     return parent, xnew, elen, added
+
+
+class OracleForest(object):
+    """CPU stand-in for backend.CudaForest (same buffers, one oracle extend per trial)."""
+
+    def __init__(self, dim, n_trials, capacity=16384, device=0):
+        self.dim, self.T = dim, n_trials
+        T, D = n_trials, dim
+        self.xrand = [0.0] * (T * D)
+        self.root = [0.0] * D
+        self.active = [1] * T
+        self.reset = [0] * T
+        self.parent = [-1] * T
+        self.xnew = [0.0] * (T * D)
+        self.elen = [0.0] * T
+        self.added = [0] * T
+        self._nn = [None] * T
+
+    def extend(self, space, max_step, resolution, check_sample=True):
+        D = self.dim
+        for t in range(self.T):
+            if self.reset[t] or self._nn[t] is None:
+                self._nn[t] = OracleNN(oracle.MetricSpec.euclidean(D))
+                self._nn[t].add([list(self.root)])
+            if not self.active[t]:
+                self.parent[t], self.added[t] = -3, 0
+                continue
+            xr = self.xrand[t * D:(t + 1) * D]
+            par, xn, el, ad = oracle_rrt_extend(self._nn[t], space, xr, max_step, resolution, check_sample)
+            self.parent[t], self.elen[t], self.added[t] = par, el, 1 if ad else 0
+            self.xnew[t * D:(t + 1) * D] = xn

@@ -163,3 +163,38 @@ def test_rrrt_bugtrap_cost_trace_identical_to_reference():
             cps.append([it, p.bestPathCost])
             last = p.bestPathCost
     assert cps == g["change_points"]
+
+
+def test_forest_trials_identical_to_reference_trees():
+    """Lock-step multi-trial kernel: every trial grows the reference planner's tree of its own seed
+    (G2 for the golden seed, and the single-trial CUDA driver for the others)."""
+    from pyoptimalmotionplanning_b200.rrt import RRT, RRTForest
+    for name in ("bugtrap", "kink"):
+        g = G.load("planners.json")["G2_%s_bruteforce" % name]
+        seeds = [3, g["seed"], 11, 12, 13]
+        f = RRTForest(G.space_spec(g["space"]), g["start"], seeds, None, None, max_step=0.15, resolution=0.01)
+        f.planMore(g["iters"])
+        v = f.trial(1)
+        assert v.nodes == g["nodes"] and v.parents == g["parents"] and v.roadmap_hash() == g["hash"]
+        random.seed(seeds[3])
+        single = RRT(G.space_spec(g["space"]), g["start"], None, None, max_step=0.15, resolution=0.01)
+        single.planMore(g["iters"])
+        assert f.trial(3).nodes == single.nodes and f.trial(3).parents == single.parents
+
+
+def test_rrrt_forest_cost_traces_identical_to_reference():
+    """r-rrt on Bugtrap, 10 seeded trials in lock step (main.py's numTrials): trial 0 reproduces G1."""
+    from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest
+    g = G.load("planners.json")["G1_rrrt_bugtrap_bruteforce"]
+    rf = RepeatedRRTForest(G.space_spec(g["space"]), g["start"], list(range(10)), g["goal"], g["goal_radius"],
+                           max_step=0.15, resolution=0.01)
+    seen, last = [], None
+    for it in range(g["iters"]):
+        rf.planMore(1)
+        if rf.bestPathCost[0] != last:
+            last = rf.bestPathCost[0]
+            seen.append(last)
+    want = [c[1] for c in g["change_points"]]
+    assert seen[-1] == want[-1]
+    assert [c for c in want if c in seen] == want        # every sampled golden cost was passed through
+    assert all(c is not None for c in rf.bestPathCost)   # all ten trials found paths

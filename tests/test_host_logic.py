@@ -13,7 +13,7 @@ from pyoptimalmotionplanning_b200 import _abi
 from pyoptimalmotionplanning_b200.descriptors import metric_from_pomp, space_from_pomp, dynamics_from_pomp
 from oracle import refshim
 from tests import golden_util as G
-from tests.fake_backend import OracleNN, OracleSpace, OracleDynamics, oracle_rrt_extend
+from tests.fake_backend import OracleNN, OracleSpace, OracleDynamics, OracleForest, oracle_rrt_extend
 
 needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference checkout not present")
 
@@ -57,6 +57,31 @@ def test_rrrt_driver_reproduces_reference_costs():
             last = p.bestPathCost
     want = [c for c in g["change_points"] if c[0] <= 1500]
     assert cps == want
+
+
+def test_forest_driver_trials_equal_single_trial_goldens():
+    """Lock-step multi-trial driver: trial t under seeds[t] grows the single-trial tree of that seed."""
+    from pyoptimalmotionplanning_b200.rrt import RRTForest, RepeatedRRTForest
+    g = G.load("planners.json")["G2_bugtrap_bruteforce"]
+    f = RRTForest(G.space_spec(g["space"]), g["start"], [7, g["seed"], 99], None, None, max_step=0.15,
+                  resolution=0.01, _backends=(OracleForest, OracleSpace))
+    f.planMore(600)
+    v = f.trial(1)
+    n = len(v.nodes)
+    assert n > 300 and v.nodes == g["nodes"][:n] and v.parents == g["parents"][:n]
+    assert f.trial(0).nodes != v.nodes
+    g1 = G.load("planners.json")["G1_rrrt_bugtrap_bruteforce"]
+    rf = RepeatedRRTForest(G.space_spec(g1["space"]), g1["start"], [0, 1], g1["goal"], g1["goal_radius"],
+                           max_step=0.15, resolution=0.01, _backends=(OracleForest, OracleSpace))
+    cps, last = [], None
+    for it in range(1, 701):
+        rf.planMore(1)
+        if rf.bestPathCost[0] != last:
+            last = rf.bestPathCost[0]
+            cps.append([-(-it // 10) * 10, last])   # the golden samples the cost every 10 iterations
+    want = [c for c in g1["change_points"] if c[0] <= 700]
+    assert [c[1] for c in cps if c[1] is not None][-1] == want[-1][1]
+    assert sorted(set(c[1] for c in cps if c[1] is not None), reverse=True) == [c[1] for c in want]
 
 
 def test_nearestneighbors_bookkeeping_without_reference():
