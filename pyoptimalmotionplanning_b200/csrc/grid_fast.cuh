@@ -649,7 +649,7 @@ __device__ __forceinline__ void flat2d_one(const GridDev& g, const double* __res
 }
 
 template <int K, int R>
-__global__ void __launch_bounds__(128, (K <= 4 ? 8 : 4))
+__global__ void __launch_bounds__(128, (K <= 4 ? 8 : 4))  // 64 regs; 48 (10 blocks/SM) spills and measured slower
 grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
                        const double* __restrict__ q, const double* __restrict__ qs, long long nq,
                        const int* __restrict__ qperm, int k, int64_t* __restrict__ out_idx,
