@@ -258,6 +258,35 @@ def run_extras(peak):
                                                     best.data_ptr(), xb.data_ptr(), db.data_ptr(), st))
     out["select_control_dubins_64"] = {"next_states_per_s": B * S / ms * 1e3, "ms": ms,
                                        "hbm_frac": B * S * 50 / (ms * 1e-3) / 1e9 / peak}
+    # Pendulum: <= 50 dependent Euler steps with sin() per candidate (FP64 latency bound)
+    dynp = DynamicsSpec(_abi.DYN_PENDULUM, 2, 2, _abi.COST_TIME, dt=0.01, p=[9.8, 1, 1])
+    mp = MetricSpec.geodesic_product([("SO2",), ("R", 1)], [1.0, 1.0]).with_cost(1.0, 3.0)
+    xp = torch.from_numpy(r2.random((B, 3)) * [6.28, 20, 1] - [0, 10, 0]).cuda()
+    xdp = torch.from_numpy(r2.random((B, 3)) * [6.28, 20, 3] - [0, 10, 0]).cuda()
+    up = torch.from_numpy(r2.random((B, S, 2)) * [0.5, 4.0] - [0, 2.0]).cuda()
+    xbp = torch.empty((B, 3), dtype=torch.float64, device="cuda")
+    cdp = CudaDynamics(dynp)
+    ms = time_cuda(lambda: cdp.select_control_device(mp, xp.data_ptr(), xdp.data_ptr(), up.data_ptr(), None, B, S,
+                                                     best.data_ptr(), xbp.data_ptr(), db.data_ptr(), st))
+    out["select_control_pendulum_64"] = {"next_states_per_s": B * S / ms * 1e3, "ms": ms,
+                                         "euler_steps_per_s": B * S * 25 / ms * 1e3}
+    # CPU port of the same two paths on a bounded sample (oracle, all host cores), for orientation
+    try:
+        from oracle import oracle as _orc
+        ns = 1 << 12
+        t0 = time.perf_counter()
+        _orc.edge_check(sp, a_h[:ns], b_h[:ns], 0.01)
+        out["cpu_port_edge_checks_kink10k_res0.01"] = {"edges_per_s": ns / (time.perf_counter() - t0),
+                                                       "sample": "%d edges, brute force over 10 K boxes as the reference does" % ns,
+                                                       "cores": os.cpu_count()}
+        nb = 1 << 13
+        xh, xdh, uh = x[:nb].cpu().numpy(), xd[:nb].cpu().numpy(), u[:nb].cpu().numpy()
+        t0 = time.perf_counter()
+        _orc.select_control(dyn, m, xh, xdh, uh)
+        out["cpu_port_select_control_dubins_64"] = {"next_states_per_s": nb * S / (time.perf_counter() - t0),
+                                                    "cores": os.cpu_count()}
+    except Exception as e:  # the oracle is optional for the product bench
+        out["cpu_port_error"] = str(e)
     # r-rrt on Bugtrap: planner iterations per second through the fused extend kernel
     import random
     from pyoptimalmotionplanning_b200.rrt import RepeatedRRT
