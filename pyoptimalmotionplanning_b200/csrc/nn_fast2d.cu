@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "grid.cuh"
 #include "grid_fast.cuh"
+#include "grid_pipe.cuh"
 #include "grid_tile.cuh"
 #include "nn_handle.cuh"
 #include "topk.cuh"
@@ -60,7 +61,21 @@ int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsor
     else GKR(KC, 3);             \
   } while (0)
   prof_begin(h, st);
-  if (KK == 1) GK(1);
+  if (KK == 1 && k == 1 && R == 1 && h->pipe_search != 0 && qsorted && qperm && !skip &&
+      h->n_dev == (int64_t)h->grid.n_indexed) {
+    // software-pipelined nearest-neighbour kernel; its overflow (block fuller than CAP, or no
+    // certificate) gets a second chance in the flat kernel (list mode), then the pruned traversal
+    constexpr int CAP = 24, TH = 128;
+    size_t psm = (size_t)2 * CAP * TH * sizeof(double2);
+    auto kern = grid_nn_pipe2d_kernel<CAP, TH>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    CUDA_TRY(cudaMemsetAsync(c2, 0, sizeof(int), st));
+    int pblocks = std::min(blocks, sm_count(h->device) * 2);
+    LAUNCH(kern, pblocks, TH, psm, st, h->grid, qsorted, qperm, (long long)nq, idx, dist, cnt, l1, c1);
+    prof_end(h, st);
+    FLAT(1, 1, (blocks + 7) / 8, npd, np, l2, c2, (const int*)l1, (const int*)c1);
+    PRUNED(1, l2, c2);
+  } else if (KK == 1) GK(1);
   else if (KK == 4) GK(4);
   else if (KK == 8) GK(8);
   else if (KK == 16) GK(16);

@@ -317,7 +317,7 @@ def test_errors_are_loud():
 
 
 @pytest.mark.parametrize("k", [1, 4, 16, 32])
-@pytest.mark.parametrize("mode", ["stream", "tile", "block", "pruned"])
+@pytest.mark.parametrize("mode", ["pipe", "stream", "tile", "block", "pruned"])
 def test_large_batch_2d_paths_match_oracle(k, mode):
     """The bucket-sorted large-batch paths (streaming TMA tile kernel / fixed-block kernel / pruned
     traversal) against the oracle on a query subset, and against each other on every query."""
@@ -329,9 +329,10 @@ def test_large_batch_2d_paths_match_oracle(k, mode):
                         rng.random((1000, 2)) * 1.2 - 0.1])
     m = MetricSpec.euclidean(2)
     nn = _nn(m, pts, grid=True)
+    nn.set_param("pipe_search", 1 if mode == "pipe" else 0)
     nn.set_param("stream_search", 1 if mode == "stream" else 0)
     nn.set_param("tile_search", 1 if mode == "tile" else 0)
-    nn.set_param("block_search", 1 if mode == "block" else 0)
+    nn.set_param("block_search", 1 if mode in ("block", "pipe") else 0)
     idx, dist, cnt = nn.knearest(q, k)
     sub = rng.choice(nq, 2500, replace=False)
     oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
@@ -339,6 +340,7 @@ def test_large_batch_2d_paths_match_oracle(k, mode):
     ref = _nn(m, pts, grid=True)
     ref.set_param("sort_queries", 0)
     ref.set_param("stream_search", 0)
+    ref.set_param("pipe_search", 0)
     ref.set_param("tile_search", 0)
     ref.set_param("block_search", 0)
     ridx, rdist, rcnt = ref.knearest(q, k)
