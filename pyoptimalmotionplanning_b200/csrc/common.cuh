@@ -86,6 +86,7 @@ struct DevBuf {
     cap = 0;
     size_t want = n + n / 4 + 16;
     cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, want * sizeof(T));  // scratch counters start from a defined state
     if (e != cudaSuccess) {
       set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
       return e == cudaErrorMemoryAllocation ? POMP_ERR_NOMEM : POMP_ERR_CUDA;

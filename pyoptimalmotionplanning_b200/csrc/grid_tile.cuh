@@ -51,6 +51,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 constexpr int TILE_RMAX = 3;
 
 template <int TW, int TH>
@@ -210,52 +224,43 @@ grid_knn_tile2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
 }
 
 // =====================================================================================================
-// Persistent, warp-specialised streaming kernel (the headline path).
+// Persistent, warp-specialised streaming kernel, v2.
 //
-// One CTA per SM loops over tiles of TW x TH cells.  A PRODUCER warp runs ahead: for each tile it
-// reads the few cell_start / qstart entries that bound the tile's halo rows and query ranges, then
-// issues cp.async.bulk (TMA) copies -- the halo rows of the bucket-sorted point array, the matching
-// slices of cell_start and the tile's bucket-sorted queries -- into one stage of a shared-memory
-// ring; all copies of a stage complete on its `full` mbarrier.  Two CONSUMER groups (4 warps each)
-// alternate tiles: one query per thread, searched entirely in shared memory (flattened (2R+1)^2
-// block + certificate, like grid_knn_flat2d_kernel), then `empty` is signalled and the producer
-// refills the stage.  HBM therefore sees a continuous stream of multi-KB sequential reads kept in
-// flight by the ring, independent of the consumers' latency.
+// One CTA per SM loops over tiles of ST_TW x ST_TH cells.  PRODUCER warps run ahead: for each tile
+// they read the cell_start entries that bound its halo rows and the tile's range in the TILE-MAJOR
+// bucket-sorted query array, then issue cp.async.bulk (TMA) copies -- one per halo row of the sorted
+// point array (~2 KB each), one for the tile's queries, one for their original indices -- into one
+// stage of a shared-memory ring; all copies of a stage complete on its `full` mbarrier.  A pool of
+// CONSUMER warps searches the staged tiles (one query per thread, flattened 3x3 block + certificate
+// as in grid_knn_flat2d_kernel, candidates read from shared memory) and signals `empty`.
+// profiles/microbench: the bulk-copy engine sustains the full HBM rate as long as a stage is <= 16
+// copies of >= 2 KB; v1 staged cell_start, sidx and per-row query slices as well (~46 small copies
+// per tile) and stalled at ~3 TB/s.
 // =====================================================================================================
-// candidates of the streaming kernel are identified by their slot in the stage's sidx slice; points
-// appended after the index build (never staged) carry their insertion index with a tag bit
-struct StageResolver {
-  const int* ssidx;
-  __device__ __forceinline__ int operator()(int p) const { return (p & 0x40000000) ? (p & 0x3fffffff) : ssidx[p]; }
-};
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 constexpr int ST_TW = 64;             // tile width in cells = query-sort bin width (shift 6)
-constexpr int ST_TH = 8;              // tile height in cell rows
+constexpr int ST_TH = 8;              // tile height in cell rows = query-sort bin height
 constexpr int ST_ROWS = ST_TH + 2 * TILE_RMAX;
-constexpr int ST_CSW = ST_TW + 16;    // cell_start ints copied per halo row (16-byte aligned slices)
-constexpr int ST_STAGES = 5;
+constexpr int ST_STAGES = 6;
 constexpr int ST_PROD_WARPS = 4;      // producers take tiles round-robin: 4 metadata round trips in flight
 constexpr int ST_CONS_WARPS = 12;     // consumer warp pool
 constexpr int ST_SLOTS = 5;           // 32-query chunk slots per tile (cap_q <= 160)
+constexpr int ST_CSTRIDE = 2;         // slot c of tile `it` belongs to consumer warp (it*ST_CSTRIDE + c) % ST_CONS_WARPS
 constexpr int ST_THREADS = 32 * (ST_PROD_WARPS + ST_CONS_WARPS);
+static_assert(ST_PROD_WARPS <= ST_STAGES, "producer run-ahead must stay within one ring revolution");
 
 struct StreamHeader {
-  int nq, fits, nrows, ylo, xal, tx0, ty0, tx1, ty1, pad;
+  int nq, fits, nrows, ylo, qbeg, qp_shift, pad0, pad1;
   int row_gs[ST_ROWS];   // first sorted position of each halo row
   int row_off[ST_ROWS];  // offset of the row in the stage's point buffer
-  int qbeg[ST_TH];       // first sorted query of each tile row
-  int qpre[ST_TH + 1];   // prefix of per-row query counts (= offset in the stage's query buffer)
-  int row_ioff[ST_ROWS]; // sidx slice of halo row r starts at ssidx[row_ioff[r]] and holds sidx[row_gs[r] & ~3 ...]
-  int qp_off[ST_TH];     // qperm slice of tile row r starts at sqperm[qp_off[r]] and holds qperm[qbeg[r] & ~3 ...]
 };
 
 struct StreamLayout {  // byte offsets inside one stage
   int cap_pts, cap_q;
-  int off_pts, off_cs, off_q, off_sidx, off_qperm, off_hdr, stage_bytes;
+  int off_pts, off_q, off_qperm, off_hdr, stage_bytes;
 };
 
 __host__ __device__ inline StreamLayout stream_layout(int cap_pts, int cap_q) {
@@ -263,27 +268,28 @@ __host__ __device__ inline StreamLayout stream_layout(int cap_pts, int cap_q) {
   L.cap_pts = cap_pts;
   L.cap_q = cap_q;
   L.off_pts = 0;
-  L.off_cs = L.off_pts + cap_pts * 16;
-  L.off_q = L.off_cs + ST_ROWS * ST_CSW * 4;
-  L.off_sidx = L.off_q + cap_q * 16;                       // per halo row: aligned slice of sidx (+3 slack each)
-  L.off_qperm = L.off_sidx + (cap_pts + 8 * ST_ROWS) * 4;  // per tile row: aligned slice of qperm
-  L.off_hdr = L.off_qperm + (cap_q + 8 * ST_TH) * 4;
+  L.off_q = L.off_pts + cap_pts * 16;
+  L.off_qperm = L.off_q + cap_q * 16;          // aligned slice of qperm (+ up to 3 leading, 3 trailing ints)
+  L.off_hdr = L.off_qperm + (cap_q + 8) * 4;
   L.stage_bytes = (L.off_hdr + (int)sizeof(StreamHeader) + 127) / 128 * 128;
   return L;
 }
 
+// qs / qperm: queries bucket-sorted by TILE (bin = tile_row * ntx + tile_col); qstart[bin] = first query
 template <int K>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 grid_knn_stream2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
                          const double* __restrict__ qs, const int* __restrict__ qperm,
-                         const int* __restrict__ qstart, int nbx, int k, int R, int cap_pts, int cap_q,
+                         const int* __restrict__ qstart, int k, int R, int cap_pts, int cap_q,
                          int64_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ out_cnt,
                          int* __restrict__ ovf_list, int* __restrict__ ovf_count) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const StreamLayout L = stream_layout(cap_pts, cap_q);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [ST_STAGES]
   uint64_t* empty = full + ST_STAGES;                      // [ST_STAGES]
-  unsigned char* stages = smem_raw + 128;
+  volatile int* seq = reinterpret_cast<volatile int*>(empty + ST_STAGES);  // tile iteration staged in each slot
+  int* done = const_cast<int*>(seq) + ST_STAGES;            // chunks of the staged tile already searched
+  unsigned char* stages = smem_raw + 256;
 
   const int W = g.ncell[0], H = g.ncell[1];
   const int ntx = (W + ST_TW - 1) / ST_TW, nty = (H + ST_TH - 1) / ST_TH;
@@ -293,7 +299,9 @@ grid_knn_stream2d_kernel(GridDev g, const double* __restrict__ pts, long long n,
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST_STAGES; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], ST_CONS_WARPS);
+      mbar_init(&empty[s], 1);
+      seq[s] = -1;
+      done[s] = 0;
     }
     fence_mbar_init();
   }
@@ -305,7 +313,13 @@ grid_knn_stream2d_kernel(GridDev g, const double* __restrict__ pts, long long n,
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
       if (it % ST_PROD_WARPS != warp) continue;
       const int s = it % ST_STAGES;
-      if (it >= ST_STAGES) mbar_wait(&empty[s], ((it / ST_STAGES) - 1) & 1);
+      if (it >= ST_STAGES) {
+        // slots are released out of order, so the parity of `empty` alone is ambiguous (fill j-2
+        // still in use looks like fill j-1 released): first wait until the previous fill of this
+        // slot has at least been STARTED (its producer published seq), then for its release
+        while (seq[s] != it - ST_STAGES) __nanosleep(32);
+        mbar_wait(&empty[s], ((it / ST_STAGES) - 1) & 1);
+      }
       unsigned char* st = stages + (size_t)s * L.stage_bytes;
       StreamHeader* hd = reinterpret_cast<StreamHeader*>(st + L.off_hdr);
       const int tcol = tile % ntx;
@@ -314,196 +328,208 @@ grid_knn_stream2d_kernel(GridDev g, const double* __restrict__ pts, long long n,
       const int xlo = max(tx0 - R, 0), xhi = min(tx1 + R, W - 1);
       const int ylo = max(ty0 - R, 0), yhi = min(ty1 + R, H - 1);
       const int nrows = yhi - ylo + 1;
-      const int xal = max(tx0 - 4, 0);
-      // query ranges of the tile rows (lanes 0..TH-1) and point ranges of the halo rows (lanes 0..nrows-1)
       int qb = 0, qn = 0;
-      if (lane < ST_TH && ty0 + lane <= ty1) {
-        qb = __ldg(qstart + (long long)(ty0 + lane) * nbx + tcol);
-        qn = __ldg(qstart + (long long)(ty0 + lane) * nbx + tcol + 1) - qb;
+      if (lane == 31) {
+        qb = __ldg(qstart + tile);
+        qn = __ldg(qstart + tile + 1) - qb;
       }
       int gs = 0, gn = 0;
       if (lane < nrows) {
         gs = __ldg(g.cell_start + (long long)(ylo + lane) * W + xlo);
         gn = __ldg(g.cell_start + (long long)(ylo + lane) * W + xhi + 1) - gs;
       }
-      int qincl = qn, gincl = gn;
+      qb = __shfl_sync(0xffffffffu, qb, 31);
+      qn = __shfl_sync(0xffffffffu, qn, 31);
+      int gincl = gn;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        int a = __shfl_up_sync(0xffffffffu, qincl, o), b = __shfl_up_sync(0xffffffffu, gincl, o);
-        if (lane >= o) {
-          qincl += a;
-          gincl += b;
-        }
+        int b = __shfl_up_sync(0xffffffffu, gincl, o);
+        if (lane >= o) gincl += b;
       }
-      const int nq = __shfl_sync(0xffffffffu, qincl, 31), npts = __shfl_sync(0xffffffffu, gincl, 31);
-      // 16-byte aligned slices of the 4-byte arrays (sidx per halo row, qperm per tile row)
-      const int gal = gs & ~3, galn = gn > 0 ? (((gs + gn + 3) & ~3) - gal) : 0;
+      const int npts = __shfl_sync(0xffffffffu, gincl, 31);
       const int qal = qb & ~3, qaln = qn > 0 ? (((qb + qn + 3) & ~3) - qal) : 0;
-      int iincl = galn, pincl = qaln;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int a = __shfl_up_sync(0xffffffffu, iincl, o), b = __shfl_up_sync(0xffffffffu, pincl, o);
-        if (lane >= o) {
-          iincl += a;
-          pincl += b;
-        }
+      const bool fits = npts <= cap_pts && qn <= cap_q;
+      // seqlock: publish "slot s now belongs to tile iteration `it`" BEFORE touching the header
+      if (lane == 0) {
+        done[s] = 0;
+        seq[s] = it;
       }
-      const int nidx = __shfl_sync(0xffffffffu, iincl, 31), nqp = __shfl_sync(0xffffffffu, pincl, 31);
-      const bool fits = npts <= cap_pts && nq <= cap_q && nidx <= cap_pts + 8 * ST_ROWS && nqp <= cap_q + 8 * ST_TH;
-      if (lane < ST_TH) {
-        hd->qbeg[lane] = qb;
-        hd->qpre[lane] = qincl - qn;
-        hd->qp_off[lane] = pincl - qaln;
-      }
-      if (lane == ST_TH) hd->qpre[ST_TH] = nq;
+      __threadfence_block();
+      __syncwarp();
       if (lane < nrows) {
         hd->row_gs[lane] = gs;
         hd->row_off[lane] = gincl - gn;
-        hd->row_ioff[lane] = iincl - galn;
       }
       if (lane == 0) {
-        hd->nq = nq;
+        hd->nq = qn;
         hd->fits = fits ? 1 : 0;
         hd->nrows = nrows;
         hd->ylo = ylo;
-        hd->xal = xal;
-        hd->tx0 = tx0;
-        hd->ty0 = ty0;
-        hd->tx1 = tx1;
-        hd->ty1 = ty1;
+        hd->qbeg = qb;
+        hd->qp_shift = qb - qal;
       }
       __syncwarp();
-      if (nq == 0 || !fits) {
-        if (lane == 0) mbar_arrive(&full[s]);  // header only
+      if (qn == 0 || !fits) {
+        if (lane == 0) {
+          mbar_arrive(&full[s]);               // header only (unfit tiles: consumers read qperm from global)
+          if (qn == 0) mbar_arrive(&empty[s]);  // nobody will search an empty tile: release the slot ourselves
+        }
         continue;
       }
-      if (lane == 0) {
-        uint32_t bytes = (uint32_t)npts * 16u + (uint32_t)nq * 16u + (uint32_t)nrows * (ST_CSW * 4u) +
-                         (uint32_t)nidx * 4u + (uint32_t)nqp * 4u;
-        mbar_expect_tx(&full[s], bytes);
-      }
+      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)npts * 16u + (uint32_t)qn * 16u + (uint32_t)qaln * 4u);
       __syncwarp();
       double2* spts = reinterpret_cast<double2*>(st + L.off_pts);
-      int* scs = reinterpret_cast<int*>(st + L.off_cs);
-      double2* sq = reinterpret_cast<double2*>(st + L.off_q);
-      if (lane < nrows) {
-        if (gn > 0) bulk_g2s(spts + (gincl - gn), g.spts + (long long)gs * 2, (uint32_t)gn * 16u, &full[s]);
-        bulk_g2s(scs + lane * ST_CSW, g.cell_start + (long long)(ylo + lane) * W + xal, ST_CSW * 4u, &full[s]);
-      }
-      if (lane < ST_TH && qn > 0) bulk_g2s(sq + (qincl - qn), qs + (long long)qb * 2, (uint32_t)qn * 16u, &full[s]);
-      int* ssidx = reinterpret_cast<int*>(st + L.off_sidx);
-      int* sqperm = reinterpret_cast<int*>(st + L.off_qperm);
-      if (lane < nrows && galn > 0) bulk_g2s(ssidx + (iincl - galn), g.sidx + gal, (uint32_t)galn * 4u, &full[s]);
-      if (lane < ST_TH && qaln > 0) bulk_g2s(sqperm + (pincl - qaln), qperm + qal, (uint32_t)qaln * 4u, &full[s]);
+      if (lane < nrows && gn > 0)
+        bulk_g2s(spts + (gincl - gn), g.spts + (long long)gs * 2, (uint32_t)gn * 16u, &full[s]);
+      if (lane == 30) bulk_g2s(st + L.off_q, qs + (long long)qb * 2, (uint32_t)qn * 16u, &full[s]);
+      if (lane == 31) bulk_g2s(st + L.off_qperm, qperm + qal, (uint32_t)qaln * 4u, &full[s]);
     }
     return;
   }
 
   // -------------------------------------------------------------------- consumers
-  // A pool of warps flows through the stages: the 32-query chunks of tile `it` are dealt to warps
-  // (rot + chunk) % NC with a rotating offset, so consecutive tiles occupy different warps and
-  // several stages are searched concurrently while others are still loading.
+  // Chunk slot c (32 queries) of tile iteration `it` belongs to warp (it*ST_CSTRIDE + c) % NC -- a
+  // static deal, so a warp visits only the tiles where it may have work and a busy warp never
+  // holds back the release of other tiles.  Because warps skip tiles, the mbarrier parity alone
+  // cannot tell "fill j done" from "fill j-1 not started": seq[s] (written by the producer before
+  // it arms the barrier) pins the ring revolution; a slot is released by whichever owner finishes
+  // the tile's last real chunk (done[s] counter), BEFORE the sidx gather and the result stores.
   const int cw = warp - ST_PROD_WARPS;
   constexpr int NC = ST_CONS_WARPS;
-  // A pool of warps flows through the stages IN LOCKSTEP ORDER (every warp waits on every tile's
-  // `full` and arrives on its `empty`, so no warp can run a whole ring ahead of the barrier phases);
-  // the 32-query chunks of a tile are dealt to warps (rot + chunk) % NC with a rotating offset, so
-  // consecutive tiles keep different warps busy.  With points, cell_start, queries, sidx and qperm all
-  // staged, a chunk is ~1 us of shared-memory work, short against the ring's refill latency.
-  int it = 0, rot = 0;
+  int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    const int c = (((cw - it * ST_CSTRIDE) % NC) + NC) % NC;
+    if (c >= ST_SLOTS) continue;
     const int s = it % ST_STAGES;
-    mbar_wait(&full[s], (it / ST_STAGES) & 1);
+    int sv;
+    while ((sv = seq[s]) < it) __nanosleep(32);
+    if (sv > it) continue;  // released and refilled without us: we had no real chunk there
+    {
+      // a warp without a real chunk here may lag by a whole ring revolution, where the parity
+      // repeats: give up as soon as the slot moves on
+      bool moved = false;
+      while (!mbar_try_wait(&full[s], (it / ST_STAGES) & 1))
+        if (seq[s] != it) {
+          moved = true;
+          break;
+        }
+      if (moved) continue;
+    }
     unsigned char* st = stages + (size_t)s * L.stage_bytes;
     const StreamHeader* hd = reinterpret_cast<const StreamHeader*>(st + L.off_hdr);
     const int nq = hd->nq;
-    const int nchunk = (nq + 31) >> 5;
-    const int first = ((cw - rot) % NC + NC) % NC;  // my first chunk of this tile
-    rot = (rot + nchunk) % NC;
-    if (first < nchunk)
-    {
-      const bool fits = hd->fits != 0;
-      const double2* spts = reinterpret_cast<const double2*>(st + L.off_pts);
-      const int* scs = reinterpret_cast<const int*>(st + L.off_cs);
-      const double2* sq = reinterpret_cast<const double2*>(st + L.off_q);
-      const int* ssidx = reinterpret_cast<const int*>(st + L.off_sidx);
-      const int* sqperm = reinterpret_cast<const int*>(st + L.off_qperm);
-      const int ylo = hd->ylo, xal = hd->xal;
-      for (int t = first * 32 + lane; t < nq; t += NC * 32) {
-        int r = 0;
-#pragma unroll
-        for (int j = 1; j < ST_TH; j++)
-          if (t >= hd->qpre[j]) r = j;
-        const int spos = hd->qbeg[r] + (t - hd->qpre[r]);
-        const long long qi = fits ? (long long)sqperm[hd->qp_off[r] + (spos - (hd->qbeg[r] & ~3))]
-                                  : (long long)__ldg(qperm + spos);
-        if (!fits) {
-          int o = atomicAdd(ovf_count, 1);
-          ovf_list[o] = (int)qi;
-          continue;
-        }
-        const double2 qv = sq[t];
-        double qq[2] = {qv.x, qv.y};
-        const int cx = grid_cell(g, 0, qq[0]), cy = grid_cell(g, 1, qq[1]);
-        typename BestList<K, StageResolver>::type top;
-        top.init(StageResolver{ssidx});
-        const int bx0 = max(cx - R, 0), bx1 = min(cx + R, W - 1);
-        for (int rr = 0; rr <= 2 * R; rr++) {
-          int y = cy + ((rr & 1) ? -((rr + 1) >> 1) : (rr >> 1));  // centre row first
-          if (y < 0 || y >= H) continue;
-          const int hr = y - ylo;
-          const int s0 = scs[hr * ST_CSW + (bx0 - xal)], e0 = scs[hr * ST_CSW + (bx1 + 1 - xal)];
-          const int gs0 = hd->row_gs[hr];
-          const int base = hd->row_off[hr] - gs0;
-          const int ibase = hd->row_ioff[hr] - (gs0 & ~3);
-          for (int pos = s0; pos < e0; pos++) {
-            if (skip && skip[ssidx[ibase + pos]]) continue;
-            const double2 pv = spts[base + pos];
-            double dx = pv.x - qq[0], dy = pv.y - qq[1];
-            double sqd = 0.0;
-            sqd = sqd + dx * dx;
-            sqd = sqd + dy * dy;
-            top.offer_sq(sqd, ibase + pos);
-          }
-        }
-        for (long long i = g.n_indexed; i < n; i++) {  // unindexed tail, straight from global memory
-          if (skip && skip[i]) continue;
-          double p2[2];
-          load_point<2>(pts, i, p2);
-          top.offer_sq(sqdist<2>(p2, qq), (int)i | 0x40000000);
-        }
-        double margin = POMP_INF;
-        {
-          int lo_c = cx - R, hi_c = cx + R;
-          if (lo_c > 0) margin = fmin(margin, qq[0] - ((g.lo[0] + (double)lo_c * g.h[0]) + g.slack[0]));
-          if (hi_c < W - 1) margin = fmin(margin, ((g.lo[0] + (double)(hi_c + 1) * g.h[0]) - g.slack[0]) - qq[0]);
-          lo_c = cy - R;
-          hi_c = cy + R;
-          if (lo_c > 0) margin = fmin(margin, qq[1] - ((g.lo[1] + (double)lo_c * g.h[1]) + g.slack[1]));
-          if (hi_c < H - 1) margin = fmin(margin, ((g.lo[1] + (double)(hi_c + 1) * g.h[1]) - g.slack[1]) - qq[1]);
-        }
-        const bool exact = !(margin < POMP_INF) || (top.T * (1.0 + 1e-9) < margin);
-        if (!exact) {
-          int o = atomicAdd(ovf_count, 1);
-          ovf_list[o] = (int)qi;
-          continue;
-        }
-        int idx[K];
-        top.finish(idx);
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++)
-          if (j < k) {
-            bool fin = top.d[j] < POMP_INF;
-            out_idx[qi * k + j] = fin ? (int64_t)idx[j] : -1;
-            out_dist[qi * k + j] = top.d[j];
-            cnt += fin;
-          }
-        if (out_cnt) out_cnt[qi] = cnt;
+    const int fits_i = hd->fits, ylo = hd->ylo, qbeg = hd->qbeg, qp_shift = hd->qp_shift;
+    __threadfence_block();
+    if (seq[s] != it) continue;  // header already belongs to a later tile (again: no real chunk of ours)
+    const int nchunk = min((nq + 31) >> 5, ST_SLOTS);  // real owners of this tile
+    if (c >= nchunk) continue;
+    if (!fits_i) {
+      // tile too dense for the stage (nothing was copied): hand all its queries to the overflow pass
+      for (int tt = c * 32 + lane; tt < nq; tt += ST_SLOTS * 32) {
+        int o = atomicAdd(ovf_count, 1);
+        ovf_list[o] = __ldg(qperm + qbeg + tt);
       }
+      __syncwarp();
+      if (lane == 0) {
+        int dprev = atomicAdd(&done[s], 1);
+        if (dprev == nchunk - 1) mbar_arrive(&empty[s]);
+      }
+      continue;
     }
+    const double2* spts = reinterpret_cast<const double2*>(st + L.off_pts);
+    const double2* sq = reinterpret_cast<const double2*>(st + L.off_q);
+    const int* sqperm = reinterpret_cast<const int*>(st + L.off_qperm) + qp_shift;
+    const int t = c * 32 + lane;
+    const bool active = t < nq;
+    long long qi = 0;
+    bool ovf = false, have = false;
+    typename BestList<K>::type top;
+    top.init(IdxResolver{g.sidx, g.n_indexed});
+    double qq[2] = {0.0, 0.0};
+    if (active) {
+      qi = sqperm[t];
+      const double2 qv = sq[t];
+      qq[0] = qv.x;
+      qq[1] = qv.y;
+      const int cx = grid_cell(g, 0, qq[0]), cy = grid_cell(g, 1, qq[1]);
+      const int x0 = max(cx - R, 0), x1 = min(cx + R, W - 1);
+      // all cell_start bounds of the block first (one round trip), then the staged candidates
+      constexpr int NRMAX = 2 * TILE_RMAX + 1;
+      int rs[NRMAX], re[NRMAX];
+#pragma unroll
+      for (int rr = 0; rr < NRMAX; rr++) {
+        int y = cy + ((rr & 1) ? -((rr + 1) >> 1) : (rr >> 1));  // centre row first
+        bool ok = rr <= 2 * R && y >= 0 && y < H;
+        long long base = (long long)(ok ? y : 0) * W;
+        int a = __ldg(g.cell_start + base + x0), b = __ldg(g.cell_start + base + x1 + 1);
+        rs[rr] = a;
+        re[rr] = ok ? b : a;
+      }
+#pragma unroll
+      for (int rr = 0; rr < NRMAX; rr++) {
+        if (rr > 2 * R) break;
+        int y = cy + ((rr & 1) ? -((rr + 1) >> 1) : (rr >> 1));
+        const int hr = min(max(y - ylo, 0), ST_ROWS - 1);
+        const int sbase = hd->row_off[hr] - hd->row_gs[hr];
+        for (int pos = rs[rr]; pos < re[rr]; pos++) {
+          if (skip && skip[__ldg(g.sidx + pos)]) continue;
+#ifdef POMP_STREAM_DEBUG
+          if (sbase + pos < 0 || sbase + pos >= cap_pts || y - ylo < 0 || y - ylo >= hd->nrows) {
+            printf("stream OOB: tile %d it %d s %d c %d t %d nq %d q(%g,%g) cx %d cy %d y %d ylo %d nrows %d hr %d "
+                   "row_off %d row_gs %d pos %d [%d,%d) seq %d\n",
+                   tile, it, s, c, t, nq, qq[0], qq[1], cx, cy, y, ylo, hd->nrows, hr, hd->row_off[hr],
+                   hd->row_gs[hr], pos, rs[rr], re[rr], seq[s]);
+            break;
+          }
+#endif
+          const double2 pv = spts[sbase + pos];
+          double dx = pv.x - qq[0], dy = pv.y - qq[1];
+          double sqd = 0.0;
+          sqd = sqd + dx * dx;
+          sqd = sqd + dy * dy;
+          top.offer_sq(sqd, pos);
+        }
+      }
+      double margin = POMP_INF;
+      {
+        int lo_c = cx - R, hi_c = cx + R;
+        if (lo_c > 0) margin = fmin(margin, qq[0] - ((g.lo[0] + (double)lo_c * g.h[0]) + g.slack[0]));
+        if (hi_c < W - 1) margin = fmin(margin, ((g.lo[0] + (double)(hi_c + 1) * g.h[0]) - g.slack[0]) - qq[0]);
+        lo_c = cy - R;
+        hi_c = cy + R;
+        if (lo_c > 0) margin = fmin(margin, qq[1] - ((g.lo[1] + (double)lo_c * g.h[1]) + g.slack[1]));
+        if (hi_c < H - 1) margin = fmin(margin, ((g.lo[1] + (double)(hi_c + 1) * g.h[1]) - g.slack[1]) - qq[1]);
+      }
+      // the unindexed tail (global memory) can only tighten T, so the certificate may use it
+      scan_tail<2>(g, pts, n, skip, qq, top);
+      const bool exact = !(margin < POMP_INF) || (top.T * (1.0 + 1e-9) < margin);
+      have = exact;
+      ovf = !exact;
+    }
+    // the staged data is no longer needed: release the slot before the global gathers / stores
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+    if (lane == 0) {
+      int dprev = atomicAdd(&done[s], 1);
+      if (dprev == nchunk - 1) mbar_arrive(&empty[s]);
+    }
+    if (ovf) {
+      int o = atomicAdd(ovf_count, 1);
+      ovf_list[o] = (int)qi;
+    }
+    if (have) {
+      int idx[K];
+      top.finish(idx);
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < K; j++)
+        if (j < k) {
+          bool fin = top.d[j] < POMP_INF;
+          out_idx[qi * k + j] = fin ? (int64_t)idx[j] : -1;
+          out_dist[qi * k + j] = top.d[j];
+          cnt += fin;
+        }
+      if (out_cnt) out_cnt[qi] = cnt;
+    }
   }
 }
 

@@ -427,6 +427,7 @@ __global__ void cell_scatter_kernel(GridDev g, const double* __restrict__ pts, l
 // keep the locality (queries of one bin touch the same few KB of sorted points) while the histogram
 // and its scan stay tiny (tens of thousands of bins instead of millions of cells).
 __global__ void query_cell_kernel(GridDev g, const double* __restrict__ q, long long nq, int D, int shift, int nbx,
+                                  int row_div,
                                   int* __restrict__ counts, int* __restrict__ qcell, int* __restrict__ slot,
                                   int* __restrict__ zero_me) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +438,7 @@ __global__ void query_cell_kernel(GridDev g, const double* __restrict__ q, long 
   int c0 = grid_cell(g, 0, p[g.gdim[0]]);
   long long row = 0;
   for (int a = 1; a < g.G; a++) row += (long long)grid_cell(g, a, p[g.gdim[a]]) * (g.stride[a] / g.ncell[0]);
-  long long b = row * nbx + (c0 >> shift);
+  long long b = (row / row_div) * nbx + (c0 >> shift);  // row_div > 1: bins are 2-D tiles (2-axis grids only)
   qcell[i] = (int)b;
   slot[i] = atomicAdd(counts + b, 1);
 }
@@ -836,6 +837,7 @@ struct SortInfo {
   const double* qsorted = nullptr;
   const int* qstart = nullptr;
   int shift = 0, nbx = 0;
+  bool tile_major = false;
 };
 
 static bool knn_is_fast(const pomp_nn* h, int k) { return is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32; }
@@ -852,18 +854,22 @@ static int grid_knn_sort(pomp_nn* h, SortScratch& S, const double* q, int64_t nq
   // 2^shift-cell bins along axis 0 (6 = the experimental tile kernels' TW)
   if (h->grid.ncell[0] >= 256) shift = (fast && h->D == 2 && h->stream_search != 0) ? 6 : (int)h->sort_shift;
   int nbx = (h->grid.ncell[0] + (1 << shift) - 1) >> shift;
-  long long nb = (h->grid.n_cells / h->grid.ncell[0]) * nbx;
+  const bool tile_major = fast && h->D == 2 && h->stream_search != 0 && shift == 6;  // bins = 64 x 8-cell tiles
+  const int row_div = tile_major ? 8 : 1;
+  long long nrow = h->grid.n_cells / h->grid.ncell[0];
+  long long nb = ((nrow + row_div - 1) / row_div) * nbx;
   POMP_TRY(S.counts.reserve((size_t)nb + 1 + (size_t)nb + 1));
   POMP_TRY(S.qcell.reserve((size_t)nq * 2));
   POMP_TRY(S.qperm.reserve((size_t)nq));
-  POMP_TRY(S.ovf.reserve((size_t)nq + 1));
+  POMP_TRY(S.ovf.reserve(2 * (size_t)nq + 2));  // two overflow lists; sized HERE: the launchers must not reallocate
+                                                 // after query_cell_kernel zeroed the first counter
   if (fast && h->D == 2) POMP_TRY(S.qsorted.reserve((size_t)nq * h->D));
   POMP_TRY(S.scan_tmp.reserve(scan_scratch_elems(nb)));
   int* counts = S.counts.p;
   int* start = S.counts.p + nb + 1;
   CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nb, st));
   int blocks = (int)((nq + 255) / 256);
-  LAUNCH(query_cell_kernel, blocks, 256, 0, st, h->grid, q, (long long)nq, h->D, shift, nbx, counts, S.qcell.p,
+  LAUNCH(query_cell_kernel, blocks, 256, 0, st, h->grid, q, (long long)nq, h->D, shift, nbx, row_div, counts, S.qcell.p,
          S.qcell.p + nq, S.ovf.p);
   S.ovf_zeroed = true;
   if (nb <= 8192) LAUNCH((scan_small_kernel<int>), 1, 1024, 0, st, counts, (int)nb, start);
@@ -876,6 +882,7 @@ static int grid_knn_sort(pomp_nn* h, SortScratch& S, const double* q, int64_t nq
   if (fast && h->D == 2) info->qsorted = S.qsorted.p;
   info->shift = shift;
   info->nbx = nbx;
+  info->tile_major = tile_major;
   return POMP_OK;
 }
 
@@ -894,11 +901,11 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
       double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
       int R = 1;
       while (R < 6 && ppc * 3.141592653589793 * R * R < 2.5 * KK + 3.0) R++;
-      if (R <= 3 && shift == 6 && h->stream_search != 0) {  // 3 = TILE_RMAX (grid_tile.cuh)
+      if (R <= 3 && shift == 6 && h->stream_search != 0 && si.tile_major) {  // 3 = TILE_RMAX (grid_tile.cuh)
         int rc = launch_grid_knn_stream2d(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
         if (rc <= 0) return rc;
       }
-      if (R <= 3 && shift == 6 && h->tile_search != 0) {
+      if (R <= 3 && shift == 6 && h->tile_search != 0 && !si.tile_major) {
         int rc = launch_grid_knn_tile2d_64(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
         if (rc <= 0) return rc;
       }

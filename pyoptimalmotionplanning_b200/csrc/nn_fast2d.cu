@@ -135,43 +135,56 @@ int pomp::launch_grid_knn_tile2d_64(pomp_nn* h, const double* q, int64_t nq, con
   return launch_grid_knn_tile2d<64>(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
 }
 
-// persistent TMA-pipelined kernel (grid_knn_stream2d_kernel): needs the 128-cell query sort
-// (sort_shift 7), ncell[0] % 4 == 0 and a padded cell_start array (build_grid provides both)
+// persistent TMA-pipelined kernel (grid_knn_stream2d_kernel v2): needs the TILE-major query sort
+// (sort_shift 6, row_div ST_TH: nn.cu sets both when stream_search is on)
 int pomp::launch_grid_knn_stream2d(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
                                    const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist,
                                    int32_t* cnt, cudaStream_t st) {
+  (void)nbx;
   const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
+  if (KK > 4) return 1;  // register lists only; larger k stays on the flat kernel
   double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
   double qdens = (double)nq / (double)h->grid.n_cells;
   int cap_pts = ((int)(1.2 * (ST_TH + 2 * R) * (ST_TW + 2 * R) * ppc) + 96 + 3) / 4 * 4;
   int cap_q = ((int)(1.5 * ST_TH * ST_TW * qdens) + 64 + 3) / 4 * 4;
   StreamLayout L = stream_layout(cap_pts, cap_q);
-  size_t smem = 128 + (size_t)ST_STAGES * L.stage_bytes;
-  if (smem > 220 * 1024 || (h->grid.ncell[0] & 3) != 0 || h->n_dev >= (1LL << 30) || cap_q > 4096)
+  size_t smem = 256 + (size_t)ST_STAGES * L.stage_bytes;
+  if (smem > 225 * 1024 || h->n_dev >= (1LL << 31) || R > TILE_RMAX || cap_q > 32 * ST_SLOTS)
     return 1;  // caller falls back
-  POMP_TRY(h->ss[h->cur].ovf.reserve((size_t)nq + 1));
-  int* ovf_count = h->ss[h->cur].ovf.p;
-  int* ovf_list = h->ss[h->cur].ovf.p + 1;
-  if (!h->ss[h->cur].ovf_zeroed) CUDA_TRY(cudaMemsetAsync(ovf_count, 0, sizeof(int), st));
+  SortScratch& S = h->ss[h->cur];
+  POMP_TRY(S.ovf.reserve(2 * (size_t)nq + 2));
+  int* c1 = S.ovf.p;
+  int* l1 = S.ovf.p + 1;
+  int* c2 = S.ovf.p + nq + 1;
+  int* l2 = S.ovf.p + nq + 2;
+  if (!S.ovf_zeroed) CUDA_TRY(cudaMemsetAsync(c1, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(c2, 0, sizeof(int), st));
   int ctas = sm_count(h->device);
-  int oblocks = std::min((int)((nq + 127) / 128), sm_count(h->device) * 4);
+  int blocks = (int)((nq + 127) / 128);
+  int oblocks = std::min(blocks, sm_count(h->device) * 4);
   const uint8_t* skip = h->skip_ptr();
+  const int* np = nullptr;
+  const double* npd = nullptr;
 #define GK(KC)                                                                                                       \
   do {                                                                                                               \
     auto kern = grid_knn_stream2d_kernel<KC>;                                                                        \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
     LAUNCH(kern, ctas, ST_THREADS, smem, st, h->grid, h->d_pts, (long long)h->n_dev, skip, qsorted, qperm, qstart,   \
-           nbx, k, R, cap_pts, cap_q, idx, dist, cnt, ovf_list, ovf_count);                                          \
+           k, R, cap_pts, cap_q, idx, dist, cnt, l1, c1);                                                            \
     prof_end(h, st);                                                                                                 \
+    /* second chance: flat kernel with the next larger block over the overflow list, then pruned */                \
+    if (R == 1)                                                                                                      \
+      LAUNCH((grid_knn_flat2d_kernel<KC, 2>), (blocks + 7) / 8, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev,  \
+             skip, q, npd, (long long)nq, np, k, idx, dist, cnt, l2, c2, (const int*)l1, (const int*)c1);            \
+    else                                                                                                             \
+      LAUNCH((grid_knn_flat2d_kernel<KC, 3>), (blocks + 7) / 8, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev,  \
+             skip, q, npd, (long long)nq, np, k, idx, dist, cnt, l2, c2, (const int*)l1, (const int*)c1);            \
     LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,     \
-           (long long)nq, (const int*)nullptr, k, idx, dist, cnt, (const int*)ovf_list, (const int*)ovf_count);      \
+           (long long)nq, np, k, idx, dist, cnt, (const int*)l2, (const int*)c2);                                    \
   } while (0)
   prof_begin(h, st);
   if (KK == 1) GK(1);
-  else if (KK == 4) GK(4);
-  else if (KK == 8) GK(8);
-  else if (KK == 16) GK(16);
-  else GK(32);
+  else GK(4);
 #undef GK
   CHECK_LAUNCH();
   return POMP_OK;

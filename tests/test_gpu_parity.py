@@ -375,3 +375,25 @@ def test_tile_path_with_masks_and_tail():
     sub = rng.choice(33000, 1500, replace=False)
     oi, od, oc = oracle.nn_knearest(m, pts, q[sub], 4, mask)
     assert (idx[sub] == oi).all() and (dist[sub] == od).all()
+
+
+def test_stream_kernel_at_bench_like_density():
+    """The persistent TMA kernel only engages when a tile's queries fit its 5 chunk slots (about 1/8 query per
+    cell, the headline configuration): exercise exactly that regime, plus a clustered region that overflows."""
+    rng = np.random.default_rng(77)
+    n, nq = 1 << 20, 1 << 16
+    pts = rng.random((n, 2))
+    pts[:30000] = 0.25 + 0.001 * rng.standard_normal((30000, 2))
+    q = rng.random((nq, 2))
+    m = MetricSpec.euclidean(2)
+    for k in (1, 4):
+        nn = _nn(m, pts, grid=True)
+        nn.set_param("stream_search", 1)
+        idx, dist, cnt = nn.knearest(q, k)
+        ref = _nn(m, pts, grid=True)
+        ref.set_param("stream_search", 0)
+        ridx, rdist, rcnt = ref.knearest(q, k)
+        assert (idx == ridx).all() and (dist == rdist).all() and (cnt == rcnt).all()
+        sub = rng.choice(nq, 800, replace=False)
+        oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
+        assert (idx[sub] == oi).all() and (dist[sub] == od).all()
