@@ -597,7 +597,7 @@ __device__ __forceinline__ bool block2d_search_nested(const GridDev& g, const do
 // qs != nullptr: queries already gathered in bucket order (coalesced).  An uncertified query is
 // retried once in place with the next larger block (rare: ~exp(-pi*ppc*R^2) of the queries for
 // k=1); only if that fails too does it go to the overflow list for the pruned traversal.
-template <int K, int R>
+template <int K, int R, bool RETRY = true>
 __device__ __forceinline__ void flat2d_one(const GridDev& g, const double* __restrict__ pts, long long n,
                                            const uint8_t* __restrict__ skip, const double (&qq)[2], long long qi,
                                            int k, int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
@@ -627,7 +627,9 @@ __device__ __forceinline__ void flat2d_one(const GridDev& g, const double* __res
     typename BestList<K>::type top;
     top.init(IdxResolver{g.sidx, g.n_indexed});
     bool exact = flat2d_search<K, R>(g, pts, n, skip, qq, cx, cy, top);
-    if (!exact) exact = block2d_search_nested<K>(g, pts, n, skip, qq, cx, cy, R + 1, top);
+    if constexpr (RETRY) {
+      if (!exact) exact = block2d_search_nested<K>(g, pts, n, skip, qq, cx, cy, R + 1, top);
+    }
     if (!exact) {
       int o = atomicAdd(ovf_count, 1);
       ovf_list[o] = (int)qi;
@@ -648,7 +650,109 @@ __device__ __forceinline__ void flat2d_one(const GridDev& g, const double* __res
   }
 }
 
-template <int K, int R>
+// Warp-cooperative retry for k = 1: the few queries whose first block gave no certificate
+// (~exp(-pi*ppc*R^2): one warp in ~15 has one) are re-searched over the (2*R2+1)^2 block by the
+// WHOLE warp, 32 candidates per pass, instead of by their own lane alone while 31 lanes idle.
+// Same arithmetic per candidate and the same (distance, insertion index) order as the lists, so
+// the answer is the one the single-thread search would give.  Every lane of the warp must call.
+__device__ __forceinline__ void warp_retry_nn2d(const GridDev& g, const double* __restrict__ pts, long long n,
+                                                const uint8_t* __restrict__ skip, bool need, double qx, double qy,
+                                                int cx, int cy, long long qi, int R2,
+                                                int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                                int32_t* __restrict__ out_cnt, int* __restrict__ ovf_list,
+                                                int* __restrict__ ovf_count) {
+  const unsigned FULL = 0xffffffffu;
+  unsigned m = __ballot_sync(FULL, need);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int W = g.ncell[0], H = g.ncell[1];
+  const double2* __restrict__ P = reinterpret_cast<const double2*>(g.spts);
+  const double2* __restrict__ PT = reinterpret_cast<const double2*>(pts);
+  const int nrow = 2 * R2 + 1;
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const double sx = __shfl_sync(FULL, qx, src), sy = __shfl_sync(FULL, qy, src);
+    const int scx = __shfl_sync(FULL, cx, src), scy = __shfl_sync(FULL, cy, src);
+    const int x0 = max(scx - R2, 0), x1 = min(scx + R2, W - 1);
+    const int y = scy - R2 + lane;
+    const bool rv = lane < nrow && y >= 0 && y < H;
+    int rs = 0, rc = 0;
+    if (rv) {
+      rs = __ldg(g.cell_start + (long long)y * W + x0);
+      rc = __ldg(g.cell_start + (long long)y * W + x1 + 1) - rs;
+    }
+    int incl = rc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int b = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += b;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int ntail = (int)(n - g.n_indexed);
+    double bd = POMP_INF;
+    int bi = 0x7fffffff;
+    for (int base = 0; base < total + ntail; base += 32) {
+      const int i = base + lane;
+      int pos = -1;
+      for (int r = 0; r < nrow; r++) {
+        const int e = __shfl_sync(FULL, incl, r), c = __shfl_sync(FULL, rc, r), s0 = __shfl_sync(FULL, rs, r);
+        if (i < e && i >= e - c) pos = s0 + (i - (e - c));
+      }
+      int oi = -1;
+      double2 pv = make_double2(0.0, 0.0);
+      if (pos >= 0) {
+        oi = __ldg(g.sidx + pos);
+        pv = __ldg(P + pos);
+      } else if (i >= total && i < total + ntail) {
+        oi = g.n_indexed + (i - total);
+        pv = __ldg(PT + oi);
+      }
+      if (oi >= 0 && !(skip && skip[oi])) {
+        double dx = pv.x - sx, dy = pv.y - sy;
+        double sq = 0.0;
+        sq = sq + dx * dx;
+        sq = sq + dy * dy;
+        const double d = sqrt(sq);
+        if (d < bd || (d == bd && oi < bi)) {
+          bd = d;
+          bi = oi;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(FULL, bd, o);
+      const int ob = __shfl_xor_sync(FULL, bi, o);
+      if (od < bd || (od == bd && ob < bi)) {
+        bd = od;
+        bi = ob;
+      }
+    }
+    if (lane == src) {
+      double margin = POMP_INF;
+      int lo_c = cx - R2, hi_c = cx + R2;
+      if (lo_c > 0) margin = fmin(margin, qx - ((g.lo[0] + (double)lo_c * g.h[0]) + g.slack[0]));
+      if (hi_c < W - 1) margin = fmin(margin, ((g.lo[0] + (double)(hi_c + 1) * g.h[0]) - g.slack[0]) - qx);
+      lo_c = cy - R2;
+      hi_c = cy + R2;
+      if (lo_c > 0) margin = fmin(margin, qy - ((g.lo[1] + (double)lo_c * g.h[1]) + g.slack[1]));
+      if (hi_c < H - 1) margin = fmin(margin, ((g.lo[1] + (double)(hi_c + 1) * g.h[1]) - g.slack[1]) - qy);
+      const bool exact = !(margin < POMP_INF) || (bd * (1.0 + 1e-9) < margin);
+      if (exact) {
+        const bool fin = bd < POMP_INF;
+        out_idx[qi] = fin ? (int64_t)bi : -1;
+        out_dist[qi] = bd;
+        if (out_cnt) out_cnt[qi] = fin ? 1 : 0;
+      } else {
+        int o = atomicAdd(ovf_count, 1);
+        ovf_list[o] = (int)qi;
+      }
+    }
+  }
+}
+
+template <int K, int R, bool RETRY = true>
 __global__ void __launch_bounds__(128, (K <= 4 ? 8 : 4))  // 64 regs; 48 (10 blocks/SM) spills and measured slower
 grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
                        const double* __restrict__ q, const double* __restrict__ qs, long long nq,
@@ -663,15 +767,48 @@ grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
       const long long qi = qlist[t];
       double2 v = __ldg(reinterpret_cast<const double2*>(q) + qi);
       double qq[2] = {v.x, v.y};
-      flat2d_one<K, R>(g, pts, n, skip, qq, qi, k, out_idx, out_dist, out_cnt, ovf_list, ovf_count);
+      flat2d_one<K, R, RETRY>(g, pts, n, skip, qq, qi, k, out_idx, out_dist, out_cnt, ovf_list, ovf_count);
     }
+    return;
+  }
+  if constexpr (K == 1 && RETRY) {
+    // k = 1: no in-thread retry; uncertified queries are retried by the whole warp afterwards
+    const bool active = t < nq;
+    long long qi = 0;
+    double qq[2] = {0.0, 0.0};
+    int cx = 0, cy = 0;
+    bool need = false;
+    if (active) {
+      qi = qperm ? (long long)__ldg(qperm + t) : t;
+      double2 v =
+          qs ? __ldg(reinterpret_cast<const double2*>(qs) + t) : __ldg(reinterpret_cast<const double2*>(q) + qi);
+      qq[0] = v.x;
+      qq[1] = v.y;
+      cx = grid_cell(g, 0, qq[0]);
+      cy = grid_cell(g, 1, qq[1]);
+      typename BestList<1>::type top;
+      top.init(IdxResolver{g.sidx, g.n_indexed});
+      if (flat2d_search<1, R>(g, pts, n, skip, qq, cx, cy, top)) {
+        int idx[1];
+        top.finish(idx);
+        const bool fin = top.d[0] < POMP_INF;
+        out_idx[qi] = fin ? (int64_t)idx[0] : -1;
+        out_dist[qi] = top.d[0];
+        if (out_cnt) out_cnt[qi] = fin ? 1 : 0;
+      } else {
+        need = true;
+      }
+    }
+    __syncwarp();
+    warp_retry_nn2d(g, pts, n, skip, need, qq[0], qq[1], cx, cy, qi, R + 1, out_idx, out_dist, out_cnt, ovf_list,
+                    ovf_count);
     return;
   }
   if (t >= nq) return;
   const long long qi = qperm ? (long long)__ldg(qperm + t) : t;
   double2 v = qs ? __ldg(reinterpret_cast<const double2*>(qs) + t) : __ldg(reinterpret_cast<const double2*>(q) + qi);
   double qq[2] = {v.x, v.y};
-  flat2d_one<K, R>(g, pts, n, skip, qq, qi, k, out_idx, out_dist, out_cnt, ovf_list, ovf_count);
+  flat2d_one<K, R, RETRY>(g, pts, n, skip, qq, qi, k, out_idx, out_dist, out_cnt, ovf_list, ovf_count);
 }
 
 template <int D, bool FILL>

@@ -1311,6 +1311,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "tile_search") h->tile_search = value;
   else if (s == "stream_search") h->stream_search = value;
   else if (s == "pipe_search") h->pipe_search = value;
+  else if (s == "two_stage") h->two_stage = value;
   else if (s == "sort_min_queries") h->sort_min_queries = value;
   else if (s == "sort_shift") h->sort_shift = value;
   else if (s == "pipeline_chunks") h->pipeline_chunks = value;

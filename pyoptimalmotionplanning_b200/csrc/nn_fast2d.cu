@@ -23,7 +23,10 @@ int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsor
   int* c2 = S.ovf.p + nq + 1;
   int* l2 = S.ovf.p + nq + 2;
   if (!S.ovf_zeroed) CUDA_TRY(cudaMemsetAsync(c1, 0, sizeof(int), st));
-  const bool two_stage = KK >= 8 && R < 3;  // k >= 8: small block first, R+1 for the few that fail
+  // small block first, R+1 (list mode) for the few that fail.  k >= 8 always; k < 8 when the
+  // two_stage knob is set (otherwise those retry inside the thread)
+  const bool small_two = KK < 8 && h->two_stage != 0 && R < 3;
+  const bool two_stage = (KK >= 8 && R < 3) || small_two;
   if (two_stage) CUDA_TRY(cudaMemsetAsync(c2, 0, sizeof(int), st));
   int blocks = (int)((nq + 127) / 128);
   int oblocks = std::min(blocks, sm_count(h->device) * 4);
@@ -42,8 +45,18 @@ int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsor
 #define PRUNED(KC, OL, OC)                                                                                         \
   LAUNCH((grid_knn_fast_kernel<2, KC>), oblocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,     \
          (long long)nq, np, k, idx, dist, cnt, (const int*)OL, (const int*)OC)
+#define FLATNR(KC, RC, NB, QS, QP, OL, OC, QL, QC)                                                                 \
+  LAUNCH((grid_knn_flat2d_kernel<(KC < 8 ? KC : 1), RC, false>), NB, 128, 0, st, h->grid, h->d_pts,                \
+         (long long)h->n_dev, skip, q, QS, (long long)nq, QP, k, idx, dist, cnt, OL, OC, QL, QC)
 #define GKR(KC, RC)                                                                                                \
   do {                                                                                                             \
+    if (small_two) {                                                                                               \
+      FLATNR(KC, RC, blocks, qsorted, qperm, l1, c1, np, np);                                                      \
+      prof_end(h, st);                                                                                             \
+      FLATNR(KC, (RC < 3 ? RC + 1 : 3), (blocks + 63) / 64, npd, np, l2, c2, (const int*)l1, (const int*)c1);      \
+      PRUNED(KC, l2, c2);                                                                                          \
+      break;                                                                                                       \
+    }                                                                                                              \
     FLAT(KC, RC, blocks, qsorted, qperm, l1, c1, np, np);                                                          \
     prof_end(h, st);                                                                                               \
     if (two_stage) {                                                                                               \
@@ -82,6 +95,7 @@ int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsor
   else GK(32);
 #undef GK
 #undef GKR
+#undef FLATNR
 #undef PRUNED
 #undef FLAT
   CHECK_LAUNCH();

@@ -49,6 +49,8 @@ struct pomp_nn {
   double max_tail = 2048;
   double stream_search = 0; // experimental: persistent TMA-pipelined kernel (grid_tile.cuh); slower than the flat
                             // kernel until the index gets a blocked layout (one bulk copy per tile)
+  double two_stage = 0;     // k < 8: 1 = uncertified queries go to a second launch (R+1, list mode) instead of
+                            // retrying inside the thread
   double pipe_search = 0;   // experimental: per-thread software pipeline over queries (grid_pipe.cuh); its
                             // 768 B/thread of cp.async slots leave 8 warps/SM -> 0.167 ms vs 0.117 ms (flat)
   double tile_search = 0;   // 2-D Euclidean, sorted queries: streaming TMA tile kernel (grid_tile.cuh)
