@@ -198,7 +198,7 @@ def run_extras(peak):
         pts = torch.from_numpy(gen_points(n, d)).cuda()
         q = torch.from_numpy(gen_queries(nq, d)).cuda()
         nn = CudaNN(MetricSpec.euclidean(d), 0)
-        for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "sort_queries", "sort_shift"):
+        for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift"):
             if "POMP_" + name.upper() in os.environ:
                 nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
         nn.set_device(pts.data_ptr(), n, st)
@@ -343,7 +343,7 @@ def run_gpu(args):
     q_slice_h = torch.from_numpy(q_all_h).pin_memory()
     pts = torch.from_numpy(pts_h).cuda(local)
     nn = CudaNN(MetricSpec.euclidean(DIM), local)
-    for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks"):
+    for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks"):
         if "POMP_" + name.upper() in os.environ:   # tuning experiments
             nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
     nn.set_device(pts.data_ptr(), n, st)

@@ -667,7 +667,9 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
     set_error("metric/point set gives no usable grid axis");
     return POMP_ERR_INVALID;
   }
-  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G <= 3 ? 2.0 : 16.0);  // measured on B200, bench extras
+  // measured on B200 (bench.py, 2^24 points): 2-D nearest 0.097 ms at 1.5 vs 0.106 ms at 2.0 points per cell
+  // (k = 16 prefers 2.0: 1.17 vs 1.44 ms -- set the points_per_cell knob for k-NN-heavy callers)
+  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G == 2 ? 1.5 : (G == 3 ? 2.0 : 16.0));
   double target = fmax(1.0, (double)n / ppc);
   target = fmin(target, 268435456.0);
   // cubic cells in metric space: ncell_a proportional to the weighted extent
@@ -917,7 +919,8 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
           double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
           // expected points inside the certified ball of radius R cells: generous for tiny k (a miss
           // costs an in-thread retry), tight for k >= 8 (misses are compacted into a second pass)
-          const double need = KK >= 8 ? 1.4 * KK + 2.0 : 2.5 * KK + 3.0;
+          double need = KK >= 8 ? 1.4 * KK + 2.0 : (KK == 1 ? 4.0 : 2.5 * KK + 3.0);  // k = 1: misses are cheap (warp retry)
+          if (KK == 1 && h->block_need > 0) need = h->block_need;
           int R = 1;
           while (R < 6 && ppc * 3.141592653589793 * R * R < need) R++;
           if (R <= 3) return launch_grid_knn_flat2d(h, q, qsorted, nq, qperm, k, R, idx, dist, cnt, st);
@@ -1312,6 +1315,8 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "stream_search") h->stream_search = value;
   else if (s == "pipe_search") h->pipe_search = value;
   else if (s == "two_stage") h->two_stage = value;
+  else if (s == "block_need") h->block_need = value;
+
   else if (s == "sort_min_queries") h->sort_min_queries = value;
   else if (s == "sort_shift") h->sort_shift = value;
   else if (s == "pipeline_chunks") h->pipeline_chunks = value;
