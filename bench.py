@@ -194,7 +194,7 @@ def run_extras(peak):
     st = torch.cuda.current_stream().cuda_stream
     out = {}
     n, nq = 1 << LOG2_N, 1 << LOG2_Q
-    for d, ks in ((2, (16,)), (3, (1, 16)), (6, (1, 16))):
+    for d, ks in ((2, (16,)), (3, (1, 16)), (4, (1, 16)), (6, (1, 16))):
         pts = torch.from_numpy(gen_points(n, d)).cuda()
         q = torch.from_numpy(gen_queries(nq, d)).cuda()
         nn = CudaNN(MetricSpec.euclidean(d), 0)
@@ -242,6 +242,40 @@ def run_extras(peak):
         out["edge_checks_kink10k_res%g" % res] = {"edges_per_s": ne / ms * 1e3, "ms": ms,
                                                   "hbm_frac": ne * 33 / (ms * 1e-3) / 1e9 / peak,
                                                   "feasible_frac": float(ok.float().mean().item())}
+    # edge set A: every roadmap sample -> its 8 nearest neighbours, as (i, j) index pairs into the
+    # sample array (the k-NN kernel builds the edge list: k = 9, the first hit is the sample itself)
+    nodes = a
+    nnr = CudaNN(MetricSpec.euclidean(2), 0)
+    nnr.set_device(nodes.data_ptr(), ne, st)
+    nnr.build_index(st)
+    kidx = torch.empty((ne, 9), dtype=torch.int64, device="cuda")
+    kdst = torch.empty((ne, 9), dtype=torch.float64, device="cuda")
+    ms_knn = time_cuda(lambda: nnr.knearest_device(nodes.data_ptr(), ne, 9, kidx.data_ptr(), kdst.data_ptr(), None, st),
+                       reps=2, warm=1)
+    ij = torch.stack([torch.arange(ne, device="cuda").repeat_interleave(8), kidx[:, 1:].reshape(-1)], 1).to(torch.int32).contiguous()
+    del kidx, kdst, nnr
+    nedge = ij.shape[0]
+    oki = torch.empty(nedge, dtype=torch.uint8, device="cuda")
+    ms = time_cuda(lambda: space.edge_check_indexed_device(nodes.data_ptr(), ij.data_ptr(), nedge, 0.01, oki.data_ptr(), st),
+                   reps=3, warm=1)
+    out["edge_checks_indexed_8nn_res0.01"] = {"edges_per_s": nedge / ms * 1e3, "ms": ms, "edges": nedge,
+                                              "hbm_frac": nedge * 41 / (ms * 1e-3) / 1e9 / peak,
+                                              "feasible_frac": float(oki.float().mean().item()),
+                                              "knn_k9_selfjoin_ms": ms_knn}
+    del ij, oki
+    # SE(2)-weighted nearest neighbour (Dubins state space metric, weights [1, 0.5/pi]), D = 3
+    pts3 = torch.from_numpy(gen_points(n, 3) * [1, 1, 2 * np.pi]).cuda()
+    q3 = torch.from_numpy(gen_queries(nq, 3) * [1, 1, 2 * np.pi]).cuda()
+    nns = CudaNN(MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi]), 0)
+    nns.set_device(pts3.data_ptr(), n, st)
+    nns.build_index(st)
+    i3 = torch.empty((nq, 1), dtype=torch.int64, device="cuda")
+    d3 = torch.empty((nq, 1), dtype=torch.float64, device="cuda")
+    ms = time_cuda(lambda: nns.knearest_device(q3.data_ptr(), nq, 1, i3.data_ptr(), d3.data_ptr(), None, st), reps=3, warm=1)
+    out["knn_SE2weighted_k1"] = {"queries_per_s": nq / ms * 1e3, "ms": ms,
+                                 "hbm_frac": (n * 24 + nq * 24 + nq * 16) / (ms * 1e-3) / 1e9 / peak}
+    del nns, pts3, q3, i3, d3
+    torch.cuda.empty_cache()
     # batched control selection, Dubins, B x 64 candidates
     B, S = 65536, 64
     dyn = DynamicsSpec(_abi.DYN_DUBINS, 3, 2, _abi.COST_ABS_U0)
@@ -258,6 +292,22 @@ def run_extras(peak):
                                                     best.data_ptr(), xb.data_ptr(), db.data_ptr(), st))
     out["select_control_dubins_64"] = {"next_states_per_s": B * S / ms * 1e3, "ms": ms,
                                        "hbm_frac": B * S * 50 / (ms * 1e-3) / 1e9 / peak}
+    for Bs in (1, 512):  # the planner-sized batches of SURVEY 8(d): launch-latency bound
+        ms = time_cuda(lambda: cd.select_control_device(m, x.data_ptr(), xd.data_ptr(), u.data_ptr(), None, Bs, S,
+                                                        best.data_ptr(), xb.data_ptr(), db.data_ptr(), st))
+        out["select_control_dubins_64_B%d" % Bs] = {"next_states_per_s": Bs * S / ms * 1e3, "ms": ms}
+    # DoubleIntegrator (closed-form constant-acceleration step, x = (q, v) in R^4, u = (dt, a) in R^3)
+    dyndi = DynamicsSpec(_abi.DYN_CV, 4, 3, _abi.COST_TIME, dt=0.05)
+    mdi = MetricSpec.euclidean(4).with_cost(1.0, 10.0)
+    xdi = torch.from_numpy(r2.random((B, 5)) * [1, 1, 2, 2, 1] - [0, 0, 1, 1, 0]).cuda()
+    xddi = torch.from_numpy(r2.random((B, 5)) * [1, 1, 2, 2, 10] - [0, 0, 1, 1, 0]).cuda()
+    udi = torch.from_numpy(r2.random((B, S, 3)) * [0.5, 10, 10] - [0, 5, 5]).cuda()
+    xbdi = torch.empty((B, 5), dtype=torch.float64, device="cuda")
+    cddi = CudaDynamics(dyndi)
+    ms = time_cuda(lambda: cddi.select_control_device(mdi, xdi.data_ptr(), xddi.data_ptr(), udi.data_ptr(), None, B, S,
+                                                      best.data_ptr(), xbdi.data_ptr(), db.data_ptr(), st))
+    out["select_control_doubleintegrator_64"] = {"next_states_per_s": B * S / ms * 1e3, "ms": ms,
+                                                 "hbm_frac": B * S * 65 / (ms * 1e-3) / 1e9 / peak}
     # Pendulum: <= 50 dependent Euler steps with sin() per candidate (FP64 latency bound)
     dynp = DynamicsSpec(_abi.DYN_PENDULUM, 2, 2, _abi.COST_TIME, dt=0.01, p=[9.8, 1, 1])
     mp = MetricSpec.geodesic_product([("SO2",), ("R", 1)], [1.0, 1.0]).with_cost(1.0, 3.0)

@@ -120,6 +120,9 @@ __device__ __forceinline__ double py_fmod(double a, double m) {
 }
 
 __device__ __forceinline__ double so2_normalize(double a) {
+  // already in (0, 2 pi): fmod returns its argument unchanged (exactly), skip the ~100-instruction
+  // software fmod -- the common case for planner states
+  if (a > 0.0 && a < POMP_TWOPI) return a;
   double res = py_fmod(a, POMP_TWOPI);
   if (res < 0) return res + POMP_TWOPI;
   return res;

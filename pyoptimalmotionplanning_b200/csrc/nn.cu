@@ -396,7 +396,7 @@ __global__ void bbox_kernel(const double* __restrict__ pts, long long n, int D, 
 
 __device__ __forceinline__ long long grid_cell_id(const GridDev& g, const double* p) {
   long long id = 0;
-  for (int a = 0; a < g.G; a++) id += (long long)grid_cell(g, a, p[g.gdim[a]]) * g.stride[a];
+  for (int a = 0; a < g.G; a++) id += (long long)grid_cell_p(g, a, p[g.gdim[a]]) * g.stride[a];
   return id;
 }
 
@@ -437,7 +437,7 @@ __global__ void query_cell_kernel(GridDev g, const double* __restrict__ q, long 
   for (int j = 0; j < D; j++) p[j] = q[i * D + j];
   int c0 = grid_cell(g, 0, p[g.gdim[0]]);
   long long row = 0;
-  for (int a = 1; a < g.G; a++) row += (long long)grid_cell(g, a, p[g.gdim[a]]) * (g.stride[a] / g.ncell[0]);
+  for (int a = 1; a < g.G; a++) row += (long long)grid_cell_p(g, a, p[g.gdim[a]]) * (g.stride[a] / g.ncell[0]);
   long long b = (row / row_div) * nbx + (c0 >> shift);  // row_div > 1: bins are 2-D tiles (2-axis grids only)
   qcell[i] = (int)b;
   slot[i] = atomicAdd(counts + b, 1);
@@ -486,7 +486,7 @@ grid_knn_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts, l
   // phase A: any k real points bound the k-th distance from above; take them next to the query's
   // home cell in the sorted order (spatially close), growing the window while masked points hide it
   long long home = 0;
-  for (int a = 0; a < g.G; a++) home += (long long)grid_cell(g, a, qq[g.gdim[a]]) * g.stride[a];
+  for (int a = 0; a < g.G; a++) home += (long long)grid_cell_p(g, a, qq[g.gdim[a]]) * g.stride[a];
   int hs = __ldg(g.cell_start + home), he = __ldg(g.cell_start + home + 1);
   int center = (hs + he) >> 1;
   int w0 = max(0, center - K), w1 = min(g.n_indexed, center + K);
@@ -620,6 +620,7 @@ static void axis_scales(const pomp_metric_desc& m, double* s /*[base_dim]*/) {
   }
 }
 
+static bool is_plain_euclid(const pomp_metric_desc& m);
 static int build_grid(pomp_nn* h, cudaStream_t st) {
   POMP_TRY(nn_flush(h, st));
   h->grid_valid = false;
@@ -662,6 +663,26 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
       G++;
     }
   }
+  // SO(2) components of a product metric become PERIODIC axes (after the Cartesian ones: axis 0,
+  // the contiguous run, is never periodic): angles are bucketed by so2.normalize over [0, 2 pi)
+  if (G > 0 && h->metric.kind == POMP_METRIC_GEODESIC_PRODUCT && h->periodic_axes != 0) {
+    int j = 0;
+    for (int c = 0; c < h->metric.n_comp; c++) {
+      if (h->metric.comp_kind[c] == POMP_COMP_SO2 && h->metric.comp_weight[c] > 0.0 && G < POMP_MAX_DIM &&
+          isfinite(lo[j]) && isfinite(hi[j])) {
+        g.gdim[G] = j;
+        g.lo[G] = 0.0;
+        g.hi[G] = 6.283185307179586;
+        g.periodic[G] = 1;
+        const double sc = sqrt(h->metric.comp_weight[c]);
+        wext[G] = 6.283185307179586 * sc;
+        g.rscale[G] = (1.0 + 1e-9) / sc;
+        g.slack[G] = 1e-8;
+        G++;
+      }
+      j += h->metric.comp_kind[c] == POMP_COMP_SO2 ? 1 : h->metric.comp_dim[c];
+    }
+  }
   if (G == 0) {
     h->grid_unusable = true;
     set_error("metric/point set gives no usable grid axis");
@@ -669,7 +690,9 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   }
   // measured on B200 (bench.py, 2^24 points): 2-D nearest 0.097 ms at 1.5 vs 0.106 ms at 2.0 points per cell
   // (k = 16 prefers 2.0: 1.17 vs 1.44 ms -- set the points_per_cell knob for k-NN-heavy callers)
-  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G == 2 ? 1.5 : (G == 3 ? 2.0 : 16.0));
+  // generic metrics (SE(2) states, 2^24 points): 3.1 ms at 2, 2.8 ms at 4 points per cell (profiles/se2_probe.py)
+  const bool generic3 = G == 3 && !is_plain_euclid(h->metric);
+  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G == 2 ? 1.5 : (G == 3 ? (generic3 ? 4.0 : 2.0) : 16.0));
   double target = fmax(1.0, (double)n / ppc);
   target = fmin(target, 268435456.0);
   // cubic cells in metric space: ncell_a proportional to the weighted extent
@@ -1316,6 +1339,10 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "pipe_search") h->pipe_search = value;
   else if (s == "two_stage") h->two_stage = value;
   else if (s == "block_need") h->block_need = value;
+  else if (s == "periodic_axes") {
+    h->periodic_axes = value;
+    h->grid_valid = false;
+  }
 
   else if (s == "sort_min_queries") h->sort_min_queries = value;
   else if (s == "sort_shift") h->sort_shift = value;
@@ -1414,11 +1441,15 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
       CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->pipe_ev.push_back(e);
     }
-    int64_t per = ((nq + nchunk - 1) / nchunk + 127) / 128 * 128;
-    for (int c = 0; c < nchunk; c++) {
-      int64_t b = (int64_t)c * per, e = std::min<int64_t>(nq, b + per);
-      if (b >= e) break;
-      int64_t m = e - b;
+    // chunk sizes shrink towards the end (weights nchunk+1, nchunk, ..., 2): the search and copy-out of
+    // the LAST chunk cannot hide behind anything, so it is the smallest (host-to-device is the slower
+    // direction on this box: 36 vs 56 GB/s, profiles/pcie_probe.py)
+    const int64_t wsum = (int64_t)nchunk * (nchunk + 3) / 2;
+    int64_t b = 0;
+    for (int c = 0; c < nchunk && b < nq; c++) {
+      int64_t m = (nq * (nchunk + 1 - c) / wsum + 127) / 128 * 128;
+      if (c == nchunk - 1 || b + m > nq) m = nq - b;
+      const int64_t e = b + m;
       CUDA_TRY(cudaMemcpyAsync(h->q_dev.p + b * h->D, q_h + b * h->D, sizeof(double) * (size_t)m * h->D,
                                cudaMemcpyHostToDevice, h->copy_in));
       CUDA_TRY(cudaEventRecord(h->pipe_ev[2 * c], h->copy_in));
@@ -1434,6 +1465,7 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
       if (count_h)
         CUDA_TRY(cudaMemcpyAsync(count_h + b, h->out_cnt.p + b, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost,
                                  h->copy_out));
+      b = e;
     }
     CUDA_TRY(cudaStreamSynchronize(h->copy_out));
     CUDA_TRY(cudaStreamSynchronize(st));

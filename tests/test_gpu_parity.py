@@ -397,3 +397,27 @@ def test_stream_kernel_at_bench_like_density():
         sub = rng.choice(nq, 800, replace=False)
         oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
         assert (idx[sub] == oi).all() and (dist[sub] == od).all()
+
+
+def test_so2_periodic_axis_wraps_and_normalises():
+    """SO(2) components are periodic grid axes: neighbours across the 0 / 2 pi seam and angles stored
+    outside [0, 2 pi) must come out exactly as the brute-force oracle finds them."""
+    m = MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi])
+    rng = np.random.default_rng(77)
+    n, nq, k = 40000, 600, 4
+    pts = rng.random((n, 3)) * [1, 1, 8 * np.pi] - [0, 0, 4 * np.pi]   # angles in [-4 pi, 4 pi)
+    q = rng.random((nq, 3)) * [1, 1, 8 * np.pi] - [0, 0, 4 * np.pi]
+    q[:200, 2] = rng.choice([0.0, 1e-9, -1e-9, 2 * np.pi, 2 * np.pi - 1e-12, -2 * np.pi], 200)  # on the seam
+    for periodic in (1.0, 0.0):
+        nn = _nn(m, None, True)
+        nn.set_param("periodic_axes", periodic)
+        nn.set(pts)
+        idx, dist, cnt = nn.knearest(q, k)
+        assert nn.get_stat("grid_axes") == (3 if periodic else 2)
+        oi, od, oc = oracle.nn_knearest(m, pts, q, k)
+        assert (cnt == oc).all()
+        assert _near_tie_ok(m, pts, q, idx, oi, od)
+        np.testing.assert_allclose(dist, od, rtol=1e-14)
+        off, hits = nn.neighbors(q[:150], 0.05)
+        ooff, ohits = oracle.nn_neighbors(m, pts, q[:150], 0.05, True)
+        assert abs(int(off[-1]) - int(ooff[-1])) <= 2
