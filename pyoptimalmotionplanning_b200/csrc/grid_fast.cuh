@@ -282,24 +282,54 @@ __device__ __forceinline__ double gap_sq(const double (&gap)[D]) {
   return s;
 }
 
-template <int D, int A>
+// CO (centre-out: 0, -1, +1, -2, ...): near cells shrink the threshold before the far ones are looked
+// at, and a direction closes at the first cell whose gap bound exceeds it (gaps grow with the
+// offset, the threshold only shrinks).  Pays when the first bound is loose -- k >= 8 in 4-D / 6-D:
+// 73 -> 49 ms for k = 16 in 6-D; for k = 1 the plain ascending sweep over the range is cheaper.
+template <int D, int A, bool CO = false>
 struct FastLevel {
   template <class C>
   static __device__ __forceinline__ void run(const GridDev& g, const uint8_t* __restrict__ skip,
                                              const double (&q)[D], double (&gap)[D], long long base, C& c, int w0,
                                              int w1) {
-    int lo, hi;
-    grid_range(g, A, q[A], c.threshold(), &lo, &hi);
-    for (int cc = lo; cc <= hi; cc++) {
-      gap[A] = grid_gap(g, A, cc, q[A]);
-      if (gap_sq<D, A>(gap) > c.tsq_up()) continue;
-      FastLevel<D, A - 1>::run(g, skip, q, gap, base + (long long)cc * g.stride[A], c, w0, w1);
+    if constexpr (CO) {
+      const int home = grid_cell(g, A, q[A]);
+      const int nc = g.ncell[A];
+      bool dlo = false, dhi = false;
+      for (int t = 0; !(dlo && dhi); t++) {
+        const int off = t == 0 ? 0 : ((t & 1) ? -((t + 1) >> 1) : (t >> 1));
+        if (off < 0 ? dlo : dhi) continue;
+        const int cc = home + off;
+        if (cc < 0) {
+          dlo = true;
+          continue;
+        }
+        if (cc >= nc) {
+          dhi = true;
+          continue;
+        }
+        gap[A] = grid_gap(g, A, cc, q[A]);
+        if (gap_sq<D, A>(gap) > c.tsq_up()) {
+          if (off < 0) dlo = true;
+          else dhi = true;
+          continue;
+        }
+        FastLevel<D, A - 1, CO>::run(g, skip, q, gap, base + (long long)cc * g.stride[A], c, w0, w1);
+      }
+    } else {
+      int lo, hi;
+      grid_range(g, A, q[A], c.threshold(), &lo, &hi);
+      for (int cc = lo; cc <= hi; cc++) {
+        gap[A] = grid_gap(g, A, cc, q[A]);
+        if (gap_sq<D, A>(gap) > c.tsq_up()) continue;
+        FastLevel<D, A - 1, CO>::run(g, skip, q, gap, base + (long long)cc * g.stride[A], c, w0, w1);
+      }
     }
   }
 };
 
-template <int D>
-struct FastLevel<D, 0> {
+template <int D, bool CO>
+struct FastLevel<D, 0, CO> {
   template <class C>
   static __device__ __forceinline__ void run(const GridDev& g, const uint8_t* __restrict__ skip,
                                              const double (&q)[D], double (&gap)[D], long long base, C& c, int w0,
@@ -374,7 +404,7 @@ __device__ __forceinline__ void knn_pruned_one(const GridDev& g, const double* _
   double gap[D];
 #pragma unroll
   for (int i = 0; i < D; i++) gap[i] = 0.0;
-  FastLevel<D, D - 1>::run(g, skip, qq, gap, 0LL, top, w0, w1);
+  FastLevel<D, D - 1, (K >= 8)>::run(g, skip, qq, gap, 0LL, top, w0, w1);
   scan_tail<D>(g, pts, n, skip, qq, top);
   int cnt = 0;
 #pragma unroll
