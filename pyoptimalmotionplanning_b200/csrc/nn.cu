@@ -692,7 +692,7 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   // (k = 16 prefers 2.0: 1.17 vs 1.44 ms -- set the points_per_cell knob for k-NN-heavy callers)
   // generic metrics (SE(2) states, 2^24 points): 3.1 ms at 2, 2.8 ms at 4 points per cell (profiles/se2_probe.py)
   const bool generic3 = G == 3 && !is_plain_euclid(h->metric);
-  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G == 2 ? 1.5 : (G == 3 ? (generic3 ? 4.0 : 2.0) : 16.0));
+  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G == 2 ? 1.5 : (G == 3 ? (generic3 ? 4.0 : 2.0) : 4.0));  // 4-D / 6-D: 4 beats 2, 8, 16 (bench extras)
   double target = fmax(1.0, (double)n / ppc);
   target = fmin(target, 268435456.0);
   // cubic cells in metric space: ncell_a proportional to the weighted extent
@@ -952,7 +952,9 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
         return launch_grid_knn_fast<2>(h, q, nq, qperm, k, idx, dist, cnt, st);
       }
       case 3:
-        return h->block_search != 0 ? launch_grid_knn_block<3>(h, q, nq, qperm, k, idx, dist, cnt, st)
+        // 3-D: the pruned traversal beats the fixed 5x5x5 block (k=1: 0.49 vs 0.61 ms, k=16: 5.1 vs 6.9 ms at
+        // 2^24 points); block_search = 2 still selects the block kernel
+        return h->block_search >= 2 ? launch_grid_knn_block<3>(h, q, nq, qperm, k, idx, dist, cnt, st)
                                     : launch_grid_knn_fast<3>(h, q, nq, qperm, k, idx, dist, cnt, st);
       case 4: return launch_grid_knn_fast<4>(h, q, nq, qperm, k, idx, dist, cnt, st);
       case 6: return launch_grid_knn_fast<6>(h, q, nq, qperm, k, idx, dist, cnt, st);

@@ -56,7 +56,7 @@ struct pomp_nn {
   double pipe_search = 0;   // experimental: per-thread software pipeline over queries (grid_pipe.cuh); its
                             // 768 B/thread of cp.async slots leave 8 warps/SM -> 0.167 ms vs 0.117 ms (flat)
   double tile_search = 0;   // 2-D Euclidean, sorted queries: streaming TMA tile kernel (grid_tile.cuh)
-  double block_search = 1;  // 2-D/3-D Euclidean: fixed block of cells + certificate (0: pruned traversal)
+  double block_search = 1;  // 2-D Euclidean: fixed block of cells + certificate (0: pruned traversal; 2: also in 3-D)
   // scratch for queries
   DevBuf<double> q_dev;
   DevBuf<double> part_d;

@@ -353,12 +353,14 @@ def test_large_batch_3d_block_path_matches_oracle():
     pts = rng.random((n, 3))
     q = rng.random((nq, 3))
     m = MetricSpec.euclidean(3)
-    nn = _nn(m, pts, grid=True)
-    for k in (1, 16):
-        idx, dist, cnt = nn.knearest(q, k)
-        sub = rng.choice(nq, 1500, replace=False)
-        oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
-        assert (idx[sub] == oi).all() and (dist[sub] == od).all()
+    sub = rng.choice(nq, 1500, replace=False)
+    for block in (2, 1):   # 2: fixed-block kernel, 1: pruned traversal (the default in 3-D)
+        nn = _nn(m, pts, grid=True)
+        nn.set_param("block_search", block)
+        for k in (1, 16):
+            idx, dist, cnt = nn.knearest(q, k)
+            oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
+            assert (idx[sub] == oi).all() and (dist[sub] == od).all()
 
 
 def test_tile_path_with_masks_and_tail():
