@@ -223,18 +223,10 @@ def run_extras(peak):
         del nn, pts, q
         torch.cuda.empty_cache()
     # Kink roadmap edge checks: 4 Mi samples, Kink's 4 boxes + 9996 small boxes, RRT-style edges <= 0.15
-    rng = np.random.default_rng(8)
-    c = rng.random((9996, 2))
-    hs = 0.001 + rng.random((9996, 2)) * 0.003
-    w = 0.02
-    kink = [[0.3, 0, 0.5 + w * 0.5, 0.2 - w * 0.5], [0.5 + w * 0.5, 0, 0.7, 0.3 - w * 0.5],
-            [0.3, 0.2 + w * 0.5, 0.5 - w * 0.5, 0.7], [0.5 - w * 0.5, 0.3 + w * 0.5, 0.7, 0.7]]
-    sp = SpaceSpec([0, 0], [1, 1], boxes=np.concatenate([np.array(kink), np.concatenate([c - hs, c + hs], 1)]))
+    sp = kink10k_space_spec()
     space = CudaSpace(sp, 0)
     ne = 1 << 22
-    a_h = np.random.default_rng(7).random((ne, 2))
-    dlt = np.random.default_rng(9).random((ne, 2)) - 0.5
-    b_h = np.clip(a_h + dlt * (0.15 / np.maximum(np.linalg.norm(dlt, axis=1, keepdims=True), 1e-12)), 0, 1)
+    a_h, b_h = rrt_edges(ne)
     a, b = torch.from_numpy(a_h).cuda(), torch.from_numpy(b_h).cuda()
     ok = torch.empty(ne, dtype=torch.uint8, device="cuda")
     for res in (0.01, 0.001):
@@ -361,6 +353,93 @@ def run_extras(peak):
         dt = time.perf_counter() - t0
         out["rrrt_bugtrap_lockstep_%dtrials" % T] = {"iters_per_s": T * its / dt, "per_trial_iters_per_s": its / dt,
                                                     "best_cost_trial0": rf.bestPathCost[0]}
+    return out
+
+
+def kink10k_space_spec():
+    """Kink's 4 boxes + 9996 small random boxes (SURVEY 8d edge bench)."""
+    from pyoptimalmotionplanning_b200 import SpaceSpec
+    rng = np.random.default_rng(8)
+    c = rng.random((9996, 2))
+    hs = 0.001 + rng.random((9996, 2)) * 0.003
+    w = 0.02
+    kink = [[0.3, 0, 0.5 + w * 0.5, 0.2 - w * 0.5], [0.5 + w * 0.5, 0, 0.7, 0.3 - w * 0.5],
+            [0.3, 0.2 + w * 0.5, 0.5 - w * 0.5, 0.7], [0.5 - w * 0.5, 0.3 + w * 0.5, 0.7, 0.7]]
+    return SpaceSpec([0, 0], [1, 1], boxes=np.concatenate([np.array(kink), np.concatenate([c - hs, c + hs], 1)]))
+
+
+def rrt_edges(ne):
+    a_h = np.random.default_rng(7).random((ne, 2))
+    dlt = np.random.default_rng(9).random((ne, 2)) - 0.5
+    b_h = np.clip(a_h + dlt * (0.15 / np.maximum(np.linalg.norm(dlt, axis=1, keepdims=True), 1e-12)), 0, 1)
+    return a_h, b_h
+
+
+def run_striped(world, rank, local, barrier):
+    """edge checks, propagation batches and planner trials are independent units --
+    every rank takes a contiguous stripe of ONE global work list, no data-path collective; the time
+    is the max over ranks, the rate is global units / that time."""
+    import torch
+    import torch.distributed as dist
+    from pyoptimalmotionplanning_b200 import MetricSpec, SpaceSpec, DynamicsSpec, _abi
+    from pyoptimalmotionplanning_b200.backend import CudaSpace, CudaDynamics
+    from pyoptimalmotionplanning_b200.sharded import stripe
+    from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ne = 1 << 22
+    b0, b1 = stripe(ne, rank, world)
+    a_h, b_h = rrt_edges(ne)
+    a, b = torch.from_numpy(a_h[b0:b1].copy()).cuda(local), torch.from_numpy(b_h[b0:b1].copy()).cuda(local)
+    ok = torch.empty(b1 - b0, dtype=torch.uint8, device="cuda")
+    space = CudaSpace(kink10k_space_spec(), local)
+    ms = timed(lambda: space.edge_check_device(a.data_ptr(), b.data_ptr(), b1 - b0, 0.01, ok.data_ptr(), st))
+    out["edge_checks_kink10k_res0.01"] = {"edges_per_s": ne / ms * 1e3, "ms": ms, "global_edges": ne}
+    B, S = 65536 * world, 64
+    s0, s1 = stripe(B, rank, world)
+    r2 = np.random.default_rng(11 + rank)
+    m = MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi]).with_cost(1.0, 3.0)
+    nb = s1 - s0
+    x = torch.from_numpy(r2.random((nb, 4)) * [1, 1, 6.28, 1]).cuda(local)
+    xd = torch.from_numpy(r2.random((nb, 4)) * [1, 1, 6.28, 3]).cuda(local)
+    u = torch.from_numpy((r2.random((nb, S, 2)) - 0.5) * [0.2, 6.28]).cuda(local)
+    best = torch.empty(nb, dtype=torch.int32, device="cuda")
+    xb = torch.empty((nb, 4), dtype=torch.float64, device="cuda")
+    db = torch.empty(nb, dtype=torch.float64, device="cuda")
+    cd = CudaDynamics(DynamicsSpec(_abi.DYN_DUBINS, 3, 2, _abi.COST_ABS_U0))
+    ms = timed(lambda: cd.select_control_device(m, x.data_ptr(), xd.data_ptr(), u.data_ptr(), None, nb, S,
+                                                best.data_ptr(), xb.data_ptr(), db.data_ptr(), st))
+    out["select_control_dubins_64"] = {"next_states_per_s": B * S / ms * 1e3, "ms": ms, "global_parents": B}
+    # planner trials: replicas only -- 64 seeded r-rrt trials per GPU, lock-step on each GPU
+    T = 64 * world
+    t0i, t1i = stripe(T, rank, world)
+    bug = SpaceSpec([0, 0], [1, 1], boxes=[[0.3, 0.3, 0.7, 0.7]])
+    rf = RepeatedRRTForest(bug, [0.1, 0.5], list(range(t0i, t1i)), [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01,
+                           device=local)
+    rf.planMore(50)
+    its = 1000
+    barrier()
+    tw = time.perf_counter()
+    rf.planMore(its)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    out["rrrt_bugtrap_lockstep_trials"] = {"iters_per_s": T * its / float(dt.item()), "global_trials": T}
     return out
 
 
@@ -491,6 +570,8 @@ def run_gpu(args):
                    "note": "capacity scaling: per-query cost of the grid index is ~independent of N, so sharding "
                            "the node set adds points, not queries/s"}
 
+    striped = run_striped(world, rank, local, barrier) if world > 1 and not args.no_extras else None
+
     if rank == 0:
         alg_bytes = n * DIM * 8 + nq * DIM * 8 + nq * K * 16
         kern_per_step = kern_ms / args.steps
@@ -512,6 +593,8 @@ def run_gpu(args):
                 "index": {"cells": nn.get_stat("n_cells"), "overflow_queries_last_step": nn.get_stat("overflow_queries")}}
         if sharded is not None:
             line["node_sharded"] = sharded
+        if striped is not None:
+            line["striped_units"] = striped
         if world == 1:
             if not args.no_extras:
                 line["extras"] = run_extras(peak)
