@@ -343,6 +343,30 @@ def run_extras(peak):
         iters += 10
     dt = time.perf_counter() - t0
     out["rrrt_bugtrap"] = {"iters_per_s": iters / dt, "best_cost": p.bestPathCost}
+    # RRT* rewire batch: the k nearest of a new node + both straight edges per neighbour in ONE
+    # call, against the reference's call pattern (1 knearest + 2k single edge checks) through the same library
+    rngw = np.random.default_rng(21)
+    tree = rngw.random((20000, 2))
+    nnw = CudaNN(MetricSpec.euclidean(2), 0)
+    nnw.set(tree)
+    kink_space = CudaSpace(kink10k_space_spec(), 0)
+    kw, reps = 20, 300
+    xs = rngw.random((reps, 2))
+    for x in xs[:20]:
+        nnw.rewire_candidates(kink_space, x, kw, 0.01)
+    t0 = time.perf_counter()
+    for x in xs:
+        nnw.rewire_candidates(kink_space, x, kw, 0.01)
+    t_batch = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for x in xs[:60]:
+        ids, _, _ = nnw.knearest(x[None, :], kw)
+        for i in ids[0]:
+            kink_space.edge_check_one(tree[i], x, 0.01)
+            kink_space.edge_check_one(x, tree[i], 0.01)
+    t_single = (time.perf_counter() - t0) / 60
+    out["rrtstar_rewire_k20"] = {"batched_calls_per_s": 1.0 / t_batch, "one_call_per_edge_per_s": 1.0 / t_single,
+                                 "us_batched": t_batch * 1e6, "us_one_call_per_edge": t_single * 1e6}
     # the same planner as 10 (main.py's numTrials) and 64 seeded trials in lock step: one launch per iteration
     from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest
     for T, its in ((10, 4000), (64, 1500)):

@@ -263,6 +263,14 @@ int pomp_rrt_extend_h(pomp_nn* h, pomp_space* s, const double* xrand_h, int chec
                       int32_t* added_h);
 
 /* ---------------------------------------------------------------- lock-step trials ------ */
+/* RRT* rewire batch.  Replaces, for one new node x, the knearest call of RRTStar.rewire
+ * (pomp/planners/rrtstarplanner.py:135-139) and the up-to-2k EpsilonEdgeChecker.feasible calls on straight edges that
+ * follow it (:150-152 neighbour -> x, :177-179 x -> neighbour) by one call: idx/dist/count as pomp_nn_knearest_h for
+ * the single query x; ok_in[j] = edge (node idx[j] -> x) feasible, ok_out[j] = edge (x -> node idx[j]) feasible, both
+ * with the reference's sampling schedule (edgechecker.py:20-30).  Entries j >= count are unspecified.  Host pointers. */
+int pomp_rewire_candidates_h(pomp_nn* h, pomp_space* s, const double* x_h, int32_t k, double resolution,
+                             int64_t* idx_h, double* dist_h, int32_t* count_h, uint8_t* ok_in_h, uint8_t* ok_out_h);
+
 /* T independent kinematic RRTs (main.py runs 10 trials per configuration, pomp/planners/test.py:8-52;
    BASELINE config 5 asks for thousands) advanced by one RRT.expand EACH in one launch: one block per
    trial over a device arena [T][capacity][dim].  Per trial the semantics are exactly those of

@@ -107,6 +107,7 @@ SIGNATURES = {
     "pomp_forest_size": (_I64, [_P, C.c_int]),
     "pomp_forest_extend_h": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _D, _D, _P, _P, _P, _P]),
     "pomp_rrt_extend_h": (C.c_int, [_P, _P, _P, C.c_int, _D, _D, _P, _P, _P, _P]),
+    "pomp_rewire_candidates_h": (C.c_int, [_P, _P, _P, C.c_int32, _D, _P, _P, _P, _P, _P]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpomp_b200.so")

@@ -146,6 +146,22 @@ class CudaNN(object):
             return off, idx[:need.value]
 
     # ---- queries, device buffers (raw pointers: torch tensors' data_ptr())
+    def rewire_candidates(self, space, x, k, resolution):
+        """pomp_rewire_candidates_h: the k nearest nodes of x plus the feasibility of the straight edges
+        node -> x (ok_in) and x -> node (ok_out), one call.  Returns (idx[c], dist[c], ok_in[c], ok_out[c])."""
+        D = self.dim
+        q = (C.c_double * D)(*[float(v) for v in x])
+        idx = np.empty(k, dtype=np.int64)
+        dist = np.empty(k, dtype=np.float64)
+        oin = np.empty(k, dtype=np.uint8)
+        oout = np.empty(k, dtype=np.uint8)
+        cnt = C.c_int32()
+        check(self.lib, self.lib.pomp_rewire_candidates_h(self._h, space._h, q, int(k), float(resolution),
+                                                          idx.ctypes.data, dist.ctypes.data, C.byref(cnt),
+                                                          oin.ctypes.data, oout.ctypes.data))
+        c = cnt.value
+        return idx[:c], dist[:c], oin[:c].astype(bool), oout[:c].astype(bool)
+
     def nearest_device(self, q_ptr, nq, idx_ptr, dist_ptr, stream=None):
         check(self.lib, self.lib.pomp_nn_nearest(self._h, C.c_void_p(q_ptr), nq, C.c_void_p(idx_ptr),
                                                  C.c_void_p(dist_ptr), C.c_void_p(stream or 0)))

@@ -188,6 +188,62 @@ POMP_API int pomp_rrt_extend_h(pomp_nn* h, pomp_space* sp, const double* xrand_h
   return POMP_OK;
 }
 
+// ============================================================================ RRT* rewire batch
+// RRTStar.rewire (pomp/planners/rrtstarplanner.py:122-187) asks for the k nearest nodes of the new
+// node and then checks, one call each, the straight edges neighbour -> new (incoming rewiring, in
+// order of accumulated cost, :147-161) and new -> neighbour (outgoing, :172-183).  Edge
+// feasibility is a pure function of the endpoints, so all 2k checks can be done up front in one
+// call; the planner's own ordering / early exits then run on the cached answers.
+__global__ void rewire_gather_kernel(const double* __restrict__ pts, int D, const int64_t* __restrict__ idx, int k,
+                                     QueryArg xnew, double* __restrict__ a, double* __restrict__ b) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * k) return;
+  const int jj = j % k, dir = j / k;  // dir 0: neighbour -> new, 1: new -> neighbour
+  const int64_t i = idx[jj];
+  for (int d = 0; d < D; d++) {
+    const double pn = i >= 0 ? pts[i * D + d] : xnew.v[d];
+    a[(long long)j * D + d] = dir == 0 ? pn : xnew.v[d];
+    b[(long long)j * D + d] = dir == 0 ? xnew.v[d] : pn;
+  }
+}
+
+POMP_API int pomp_rewire_candidates_h(pomp_nn* h, pomp_space* sp, const double* x_h, int32_t k, double resolution,
+                                      int64_t* idx_h, double* dist_h, int32_t* count_h, uint8_t* ok_in_h,
+                                      uint8_t* ok_out_h) {
+  POMP_REQUIRE(h && sp && x_h && idx_h && dist_h && count_h && ok_in_h && ok_out_h,
+               "NULL argument to pomp_rewire_candidates_h");
+  POMP_REQUIRE(k >= 1 && k <= 128, "k=%d outside 1..128", k);
+  POMP_REQUIRE(sp->dev.dim == h->D, "space dim %d != point dim %d", sp->dev.dim, h->D);
+  POMP_REQUIRE(resolution > 0.0, "resolution must be positive");
+  POMP_REQUIRE(sp->device == h->device, "space and index live on different devices");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  cudaStream_t st = h->stream;
+  const int D = h->D;
+  POMP_TRY(h->q_dev.reserve((size_t)D));
+  POMP_TRY(h->out_idx.reserve((size_t)k));
+  POMP_TRY(h->out_dist.reserve((size_t)k));
+  POMP_TRY(h->out_cnt.reserve(1));
+  POMP_TRY(h->rw_ab.reserve((size_t)4 * k * D));
+  POMP_TRY(h->rw_ok.reserve((size_t)2 * k));
+  CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, x_h, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+  POMP_TRY(pomp_nn_knearest(h, h->q_dev.p, 1, k, h->out_idx.p, h->out_dist.p, h->out_cnt.p, st));
+  QueryArg qa;
+  for (int j = 0; j < POMP_MAX_DIM; j++) qa.v[j] = j < D ? x_h[j] : 0.0;
+  double* a = h->rw_ab.p;
+  double* b = h->rw_ab.p + (size_t)2 * k * D;
+  LAUNCH(rewire_gather_kernel, (2 * k + 63) / 64, 64, 0, st, h->d_pts, D, h->out_idx.p, k, qa, a, b);
+  CHECK_LAUNCH();
+  POMP_TRY(pomp_edge_check(sp, a, b, 2 * k, resolution, h->rw_ok.p, st));
+  CUDA_TRY(cudaMemcpyAsync(idx_h, h->out_idx.p, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(dist_h, h->out_dist.p, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(count_h, h->out_cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(ok_in_h, h->rw_ok.p, (size_t)k, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(ok_out_h, h->rw_ok.p + k, (size_t)k, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return POMP_OK;
+}
+
 // ============================================================================ forest: lock-step trials
 // T independent kinematic RRTs advanced by one RRT.expand each in ONE launch (one block per
 // trial).  The planner loop is latency bound (one launch + one sync per iteration, tiny trees);

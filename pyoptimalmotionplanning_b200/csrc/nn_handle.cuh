@@ -76,6 +76,8 @@ struct pomp_nn {
   DevBuf<double> out_dist;
   DevBuf<int32_t> out_cnt;
   DevBuf<int64_t> out_off;
+  DevBuf<double> rw_ab;     // pomp_rewire_candidates_h: the 2k edges (a then b)
+  DevBuf<uint8_t> rw_ok;
   // pinned mailbox for the single-query fast path
   void* mailbox_h = nullptr;
   void* mailbox_d = nullptr;

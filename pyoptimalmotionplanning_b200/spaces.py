@@ -48,6 +48,7 @@ class DeviceSpace(object):
         if cur.lo != self.spec.lo or cur.hi != self.spec.hi:
             self.spec.lo, self.spec.hi = cur.lo, cur.hi
             self._be.set_bounds(cur.lo, cur.hi)
+            self.bounds_version = getattr(self, "bounds_version", 0) + 1
 
     def feasible(self, x):
         self._refresh_bounds()
@@ -70,6 +71,23 @@ class EpsilonEdgeChecker(object):
         self.resolution = resolution
         self._dev = space if isinstance(space, DeviceSpace) else DeviceSpace(space, device, _backend_factory)
         self._geo_cache = {}
+        self._rewire = None      # (resolution, {(tuple(a), tuple(b)): feasible}) of the last rewire batch
+        self.rewire_hits = 0
+
+    # ---- RRT* rewire batch (filled by NearestNeighbors.knearest, see enable_rewire_prefetch)
+    def prefetch_ready(self, nn_backend):
+        """The batch call needs both back ends on the device library (or both test fakes)."""
+        self._dev._refresh_bounds()
+        return hasattr(nn_backend, "rewire_candidates") and self._dev._be is not None
+
+    def prime(self, x, neighbours, ok_in, ok_out):
+        tx = tuple(x)
+        cache = {}
+        for p, a, b in zip(neighbours, ok_in, ok_out):
+            tp = tuple(p)
+            cache[(tp, tx)] = bool(a)
+            cache[(tx, tp)] = bool(b)
+        self._rewire = (self.resolution, cache, getattr(self._dev, "bounds_version", 0))
 
     # ---- reference API
     def feasible(self, interpolator):
@@ -77,6 +95,12 @@ class EpsilonEdgeChecker(object):
         self._dev._refresh_bounds()
         name = type(interpolator).__name__
         if name == "LinearInterpolator":  # interpolators.py:28-35
+            if (self._rewire is not None and self._rewire[0] == self.resolution
+                    and self._rewire[2] == getattr(self._dev, "bounds_version", 0)):
+                hit = self._rewire[1].get((tuple(interpolator.a), tuple(interpolator.b)))
+                if hit is not None:
+                    self.rewire_hits += 1
+                    return hit
             return be.edge_check_one(interpolator.a, interpolator.b, self.resolution)
         if name == "PiecewiseLinearInterpolator" and interpolator.trajectory is None:  # :73-102
             path = interpolator.path

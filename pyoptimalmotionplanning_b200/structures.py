@@ -37,7 +37,16 @@ class NearestNeighbors(object):
         self._be = None
         self._sig = None
         self._dim = metric.dim if isinstance(metric, MetricSpec) else None
+        self._rewire_checker = None
         self._clear_host()
+
+    def enable_rewire_prefetch(self, checker):
+        """RRT* rewire batch (rrtstarplanner.py:122-187): `checker` is this package's EpsilonEdgeChecker.
+        From now on knearest(pt, k) also decides, in the same device call, the straight edges between pt and
+        each of its k neighbours (both directions); the checker serves the planner's following
+        feasible(LinearInterpolator) calls from that batch.  Results are identical (edge feasibility is a
+        pure function of the endpoints); pass None to switch it off."""
+        self._rewire_checker = checker
 
     # ------------------------------------------------------------------ host bookkeeping
     def _clear_host(self):
@@ -183,6 +192,14 @@ class NearestNeighbors(object):
             if base is not None:
                 self._be.set_mask(base)
             if k <= 128:
+                chk = self._rewire_checker
+                if chk is not None and base is None and chk.prefetch_ready(self._be):
+                    # RRT* rewire batch: the same k nearest plus both straight edges per neighbour in ONE call;
+                    # the checker answers the planner's following feasible() calls from this batch
+                    ids, _, ok_in, ok_out = self._be.rewire_candidates(chk._dev._be, pt, k, chk.resolution)
+                    res = [(self._points[int(i)], self._datas[int(i)]) for i in ids]
+                    chk.prime(pt, [r[0] for r in res], ok_in, ok_out)
+                    return res
                 ids, _, cnt = self._be.knearest(q, k)
                 return [(self._points[int(i)], self._datas[int(i)]) for i in ids[0, :int(cnt[0])]]
             # very large k: peel off 128 at a time by masking what was already returned

@@ -71,6 +71,16 @@ class OracleNN(object):
     def neighbors(self, q, radius, inclusive=True):
         return oracle.nn_neighbors(self.spec, self.pts, q, radius, inclusive, self._mask())
 
+    def rewire_candidates(self, space, x, k, res):
+        ids, dist, cnt = oracle.nn_knearest(self.spec, self.pts, [list(x)], k, self._mask())
+        c = int(cnt[0])
+        ids, dist = ids[0, :c], dist[0, :c]
+        nb = self.pts[ids]
+        xs = np.repeat(np.asarray([list(x)], dtype=np.float64), c, 0)
+        ok_in = oracle.edge_check(space.spec, nb, xs, res) if c else np.zeros(0, bool)
+        ok_out = oracle.edge_check(space.spec, xs, nb, res) if c else np.zeros(0, bool)
+        return ids, dist, np.asarray(ok_in, bool), np.asarray(ok_out, bool)
+
 
 class OracleSpace(object):
     def __init__(self, spec, device=0):

@@ -423,3 +423,33 @@ def test_so2_periodic_axis_wraps_and_normalises():
         off, hits = nn.neighbors(q[:150], 0.05)
         ooff, ohits = oracle.nn_neighbors(m, pts, q[:150], 0.05, True)
         assert abs(int(off[-1]) - int(ooff[-1])) <= 2
+
+
+def test_rewire_candidates_match_oracle():
+    """pomp_rewire_candidates_h (RRT* rewire batch): k nearest of the new node + both straight edges per
+    neighbour, against the oracle's knearest and edge checks."""
+    from pyoptimalmotionplanning_b200.backend import CudaNN, CudaSpace
+    rng = np.random.default_rng(12)
+    boxes = np.concatenate([rng.random((60, 2)) * 0.9, np.zeros((60, 2))], 1)
+    boxes[:, 2:] = boxes[:, :2] + 0.02 + rng.random((60, 2)) * 0.06
+    for D, sp in ((2, SpaceSpec([0, 0], [1, 1], boxes=boxes)),
+                  (3, SpaceSpec([0, 0, 0], [1, 1, 1], boxes=np.array([[0.3, 0.3, 0.7, 0.7]])))):
+        m = MetricSpec.euclidean(D)
+        pts = rng.random((3000, D))
+        nn = CudaNN(m, 0)
+        nn.set(pts)
+        space = CudaSpace(sp, 0)
+        for k in (1, 7, 20):
+            for _ in range(12):
+                x = rng.random(D)
+                ids, dist, ok_in, ok_out = nn.rewire_candidates(space, x, k, 0.01)
+                oi, od, oc = oracle.nn_knearest(m, pts, [x], k)
+                assert len(ids) == int(oc[0]) == k
+                assert (ids == oi[0]).all() and (dist == od[0]).all()
+                xs = np.repeat(x[None, :], k, 0)
+                assert (ok_in == oracle.edge_check(sp, pts[ids], xs, 0.01)).all()
+                assert (ok_out == oracle.edge_check(sp, xs, pts[ids], 0.01)).all()
+    few = CudaNN(MetricSpec.euclidean(2), 0)
+    few.set(pts[:3, :2])
+    ids, dist, ok_in, ok_out = few.rewire_candidates(CudaSpace(SpaceSpec([0, 0], [1, 1]), 0), [0.5, 0.5], 8, 0.01)
+    assert len(ids) == 3 and ok_in.all() and ok_out.all()

@@ -285,6 +285,56 @@ def test_unmodified_ao_rrt_dubins_with_dropins_matches_bruteforce_reference():
 
 
 @needs_ref
+def test_unmodified_rrt_star_with_rewire_batch_matches_reference():
+    """rrt* on Kink: knearest + the straight edges to / from every neighbour decided in one
+    back-end call, then the reference's own rewire logic running on those cached answers -- same tree,
+    same costs as the unmodified reference with its kd-tree, and far fewer edge-check calls."""
+    refshim.load()
+    from pomp.example_problems import geometric
+    calls = {}
+
+    def make(mode):
+        random.seed(3)
+        prob = geometric.kinkTest()
+        if mode == "ref":
+            return prob.planner("rrt*", nearestNeighborMethod="kdtree")
+        chk = fake_checker(prob.configurationSpace, 0.01)
+        planner = prob.planner("rrt*", nearestNeighborMethod="b200", checker=chk)
+        be = chk._dev._be
+        orig = be.edge_check_one
+        calls[mode] = [0, chk]
+
+        def counted(a, b, res, _o=orig, _c=calls[mode]):
+            _c[0] += 1
+            return _o(a, b, res)
+        be.edge_check_one = counted
+        if mode == "batch":
+            planner.nearestNeighbors.enable_rewire_prefetch(chk)
+        return planner
+
+    class Chunked(object):   # planMore returns at every improvement (rrtstarplanner.py:86-90): keep going
+        def __init__(self, p):
+            self.p = p
+
+        def planMore(self, iters):
+            for _ in range(iters // 10):
+                self.p.planMore(10)
+
+        def __getattr__(self, k):
+            return getattr(self.p, k)
+
+    h_ref, n_ref, p_ref = _run_ref_planner(lambda: Chunked(make("ref")), 800, False)
+    h_one, n_one, p_one = _run_ref_planner(lambda: Chunked(make("single")), 800, True)
+    h_new, n_new, p_new = _run_ref_planner(lambda: Chunked(make("batch")), 800, True)
+    assert (h_new, n_new) == (h_ref, n_ref) == (h_one, n_one) and n_ref > 100
+    assert p_new.bestPathCost == p_ref.bestPathCost
+    costs = lambda p: sorted(n.c for n in p.nodes) if hasattr(p, "nodes") else None
+    assert costs(p_new) == costs(p_ref)
+    assert calls["batch"][1].rewire_hits > 0
+    assert calls["batch"][0] < calls["single"][0]      # the rewire edges no longer cost a call each
+
+
+@needs_ref
 def test_edge_checker_dispatch_on_reference_interpolators():
     refshim.load()
     from pomp.spaces.edgechecker import EpsilonEdgeChecker as RefChecker
