@@ -220,6 +220,11 @@ def run_extras(peak):
             ms = time_cuda(lambda: nn.neighbors_device(q.data_ptr(), nq, r, True, off.data_ptr(), hits.data_ptr(),
                                                        hits.numel(), st))
             out["radius_D2_16hits"] = {"queries_per_s": nq / ms * 1e3, "ms": ms, "hits": int(off[-1].item())}
+            dens = torch.empty(nq, dtype=torch.float64, device="cuda")
+            ms = time_cuda(lambda: nn.density_device(q.data_ptr(), nq, r, r / 4, True, dens.data_ptr(), None, st))
+            out["est_density_D2_16hits"] = {"queries_per_s": nq / ms * 1e3, "ms": ms,
+                                            "mean_density": float(dens.mean().item())}
+            del off, hits, dens
         del nn, pts, q
         torch.cuda.empty_cache()
     # Kink roadmap edge checks: 4 Mi samples, Kink's 4 boxes + 9996 small boxes, RRT-style edges <= 0.15

@@ -263,6 +263,16 @@ int pomp_rrt_extend_h(pomp_nn* h, pomp_space* s, const double* xrand_h, int chec
                       int32_t* added_h);
 
 /* ---------------------------------------------------------------- lock-step trials ------ */
+/* Gaussian kernel density of EST: density[i] = sum over the nodes p with metric(p, q_i) <= radius
+ * (inclusive != 0) or < radius of exp(-(metric(p, q_i)/sigma)^2); count[i] (nullable) = number of such nodes.  Replaces
+ * ESTKinodynamicPlanner.density (pomp/planners/kinodynamicplanner.py:688-693: neighbors(x, 4*radius), then the Python
+ * sum) and the neighbour loop of onAddNode (:676-686).  The hits are folded on the fly, nothing is materialised.  The
+ * summation order is not the reference's (which itself depends on the NN method): agreement to ~1e-13 relative. */
+int pomp_nn_density(pomp_nn* h, const double* q, int64_t nq, double radius, double sigma, int inclusive,
+                    double* density, int32_t* count, void* stream);
+int pomp_nn_density_h(pomp_nn* h, const double* q_h, int64_t nq, double radius, double sigma, int inclusive,
+                      double* density_h, int32_t* count_h);
+
 /* RRT* rewire batch.  Replaces, for one new node x, the knearest call of RRTStar.rewire
  * (pomp/planners/rrtstarplanner.py:135-139) and the up-to-2k EpsilonEdgeChecker.feasible calls on straight edges that
  * follow it (:150-152 neighbour -> x, :177-179 x -> neighbour) by one call: idx/dist/count as pomp_nn_knearest_h for

@@ -221,3 +221,22 @@ def rrt_extend(m, pts, s, xrand, max_step, res, mask=None):
     lib().orc_rrt_extend(C.byref(m.desc()), _p(pts), C.c_int64(len(pts)), _p(mask), C.byref(d), _p(xrand),
                          C.c_double(max_step), C.c_double(res), C.byref(parent), _p(xnew), C.byref(added))
     return parent.value, xnew, bool(added.value)
+
+
+def nn_density(metric_spec, pts, q, radius, sigma, inclusive=True, mask=None):
+    """ESTKinodynamicPlanner.density (pomp/planners/kinodynamicplanner.py:688-693): neighbors(x, radius), then
+    d += math.exp(-(dist/sigma)**2) over the hits, here in insertion order.  Returns (density[nq], count[nq])."""
+    import math
+    pts = np.asarray(pts, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64).reshape(-1, pts.shape[1])
+    off, hits = nn_neighbors(metric_spec, pts, q, radius, inclusive, mask)
+    dens = np.zeros(len(q))
+    cnt = np.zeros(len(q), dtype=np.int32)
+    for i in range(len(q)):
+        d = 0.0
+        for j in hits[off[i]:off[i + 1]]:
+            dist = float(metric(metric_spec, pts[j], q[i]))
+            d += math.exp(-(dist / sigma) ** 2)
+        dens[i] = d
+        cnt[i] = off[i + 1] - off[i]
+    return dens, cnt

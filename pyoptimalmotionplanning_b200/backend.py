@@ -146,6 +146,21 @@ class CudaNN(object):
             return off, idx[:need.value]
 
     # ---- queries, device buffers (raw pointers: torch tensors' data_ptr())
+    def density(self, q, radius, sigma, inclusive=True):
+        """pomp_nn_density_h: (density[nq], count[nq]) -- Gaussian kernel density of EST."""
+        q = _f64(q, self.dim)
+        nq = len(q)
+        dens = np.empty(nq, dtype=np.float64)
+        cnt = np.empty(nq, dtype=np.int32)
+        check(self.lib, self.lib.pomp_nn_density_h(self._h, _ptr(q), nq, float(radius), float(sigma),
+                                                   1 if inclusive else 0, _ptr(dens), _ptr(cnt)))
+        return dens, cnt
+
+    def density_device(self, q_ptr, nq, radius, sigma, inclusive, dens_ptr, cnt_ptr=None, stream=None):
+        check(self.lib, self.lib.pomp_nn_density(self._h, C.c_void_p(q_ptr), nq, float(radius), float(sigma),
+                                                 1 if inclusive else 0, C.c_void_p(dens_ptr), C.c_void_p(cnt_ptr or 0),
+                                                 C.c_void_p(stream or 0)))
+
     def rewire_candidates(self, space, x, k, resolution):
         """pomp_rewire_candidates_h: the k nearest nodes of x plus the feasibility of the straight edges
         node -> x (ok_in) and x -> node (ok_out), one call.  Returns (idx[c], dist[c], ok_in[c], ok_out[c])."""

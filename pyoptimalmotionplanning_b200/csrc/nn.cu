@@ -585,6 +585,78 @@ grid_radius_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts
   else counts[qi] = (int)coll.cnt;
 }
 
+// ---- Gaussian kernel density (EST): sum over the points within `radius` of exp(-(d/sigma)^2) ------
+// pomp/planners/kinodynamicplanner.py:688-693 (EST.density) and :676-686 (onAddNode): a radius query
+// whose hits are folded into one number, so nothing is materialised.
+struct DensityColl {
+  double radius, inv_sigma;
+  int inclusive;
+  double sum;
+  int cnt;
+  __device__ __forceinline__ double threshold() const { return radius; }
+  __device__ __forceinline__ void add(double d) {
+    bool hit = inclusive ? (d <= radius) : (d < radius);
+    if (hit) {
+      double t = d * inv_sigma;
+      sum += exp(-(t * t));
+      cnt++;
+    }
+  }
+  __device__ __forceinline__ void offer(double d, long long) { add(d); }
+};
+
+__global__ void __launch_bounds__(128)
+grid_density_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts, long long n,
+                    const uint8_t* __restrict__ skip, const double* __restrict__ q, long long nq, double radius,
+                    double sigma, int inclusive, double* __restrict__ dens, int32_t* __restrict__ cnt) {
+  long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const int dim = m.dim;
+  double qq[POMP_MAX_DIM];
+#pragma unroll
+  for (int j = 0; j < POMP_MAX_DIM; j++) qq[j] = j < dim ? q[qi * dim + j] : 0.0;
+  DensityColl coll{radius, 1.0 / sigma, inclusive, 0.0, 0};
+  grid_visit<0, false>(g, m, skip, qq, coll, 0, 0);
+  for (long long i = g.n_indexed; i < n; i++) {
+    if (skip && skip[i]) continue;
+    double p[POMP_MAX_DIM];
+    for (int j = 0; j < dim; j++) p[j] = __ldg(pts + i * dim + j);
+    coll.add(metric_eval(m, p, qq));
+  }
+  dens[qi] = coll.sum;
+  if (cnt) cnt[qi] = coll.cnt;
+}
+
+// small point sets: warp per query, lanes stride over the points
+__global__ void bf_density_kernel(const double* __restrict__ pts, long long n, pomp_metric_desc m,
+                                  const uint8_t* __restrict__ skip, const double* __restrict__ q, long long nq,
+                                  double radius, double sigma, int inclusive, double* __restrict__ dens,
+                                  int32_t* __restrict__ cnt) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= nq) return;
+  const int D = m.dim;
+  double qq[POMP_MAX_DIM], p[POMP_MAX_DIM];
+  load_q(q + warp * D, D, qq);
+  DensityColl coll{radius, 1.0 / sigma, inclusive, 0.0, 0};
+  for (long long i = lane; i < n; i += 32) {
+    if (skip && skip[i]) continue;
+    for (int j = 0; j < D; j++) p[j] = __ldg(pts + i * D + j);
+    coll.add(metric_eval(m, p, qq));
+  }
+  double s = coll.sum;
+  int c = coll.cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(FULL_MASK, s, o);
+    c += __shfl_xor_sync(FULL_MASK, c, o);
+  }
+  if (lane == 0) {
+    dens[warp] = s;
+    if (cnt) cnt[warp] = c;
+  }
+}
+
 // ============================================================================ host: grid build
 static void axis_scales(const pomp_metric_desc& m, double* s /*[base_dim]*/) {
   int d = base_dim(m);
@@ -1153,6 +1225,24 @@ static int radius_device(pomp_nn* h, const double* q, int64_t nq, double radius,
   return POMP_OK;
 }
 
+static int density_device(pomp_nn* h, const double* q, int64_t nq, double radius, double sigma, int inclusive,
+                          double* dens, int32_t* cnt, cudaStream_t st) {
+  if (nq == 0) return POMP_OK;
+  POMP_TRY(nn_flush(h, st));
+  bool use_grid = false;
+  POMP_TRY(want_grid(h, nq, &use_grid, st));
+  const uint8_t* skip = h->skip_ptr();
+  if (use_grid) {
+    LAUNCH(grid_density_kernel, (int)((nq + 127) / 128), 128, 0, st, h->grid, h->metric, h->d_pts, (long long)h->n_dev,
+           skip, q, (long long)nq, radius, sigma, inclusive, dens, cnt);
+  } else {
+    LAUNCH(bf_density_kernel, (int)((nq * 32 + 255) / 256), 256, 0, st, h->d_pts, (long long)h->n_dev, h->metric, skip, q,
+           (long long)nq, radius, sigma, inclusive, dens, cnt);
+  }
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
 // ============================================================================ C ABI
 POMP_API int pomp_nn_create(const pomp_metric_desc* metric, int64_t capacity_hint, int device, pomp_nn** out) {
   POMP_REQUIRE(out != nullptr, "out is NULL");
@@ -1520,6 +1610,35 @@ POMP_API int pomp_nn_neighbors(pomp_nn* h, const double* q, int64_t nq, double r
   DeviceGuard g(h->device);
   if (!g.ok) return POMP_ERR_CUDA;
   return radius_device(h, q, nq, radius, inclusive, offsets, idx, idx_capacity, needed_h, (cudaStream_t)stream);
+}
+
+POMP_API int pomp_nn_density(pomp_nn* h, const double* q, int64_t nq, double radius, double sigma, int inclusive,
+                             double* density, int32_t* count, void* stream) {
+  POMP_REQUIRE(h && (nq == 0 || (q && density)) && nq >= 0, "bad arguments to pomp_nn_density");
+  POMP_REQUIRE(radius >= 0.0 && sigma > 0.0, "density needs radius >= 0 and sigma > 0");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  return density_device(h, q, nq, radius, sigma, inclusive, density, count, (cudaStream_t)stream);
+}
+
+POMP_API int pomp_nn_density_h(pomp_nn* h, const double* q_h, int64_t nq, double radius, double sigma, int inclusive,
+                               double* density_h, int32_t* count_h) {
+  POMP_REQUIRE(h && (nq == 0 || (q_h && density_h)) && nq >= 0, "bad arguments to pomp_nn_density_h");
+  POMP_REQUIRE(radius >= 0.0 && sigma > 0.0, "density needs radius >= 0 and sigma > 0");
+  DeviceGuard g(h->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (nq == 0) return POMP_OK;
+  cudaStream_t st = h->stream;
+  POMP_TRY(h->q_dev.reserve((size_t)nq * h->D));
+  POMP_TRY(h->out_dist.reserve((size_t)nq));
+  POMP_TRY(h->out_cnt.reserve((size_t)nq));
+  CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, q_h, sizeof(double) * (size_t)nq * h->D, cudaMemcpyHostToDevice, st));
+  POMP_TRY(density_device(h, h->q_dev.p, nq, radius, sigma, inclusive, h->out_dist.p, h->out_cnt.p, st));
+  CUDA_TRY(cudaMemcpyAsync(density_h, h->out_dist.p, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+  if (count_h)
+    CUDA_TRY(cudaMemcpyAsync(count_h, h->out_cnt.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return POMP_OK;
 }
 
 POMP_API int pomp_nn_neighbors_h(pomp_nn* h, const double* q_h, int64_t nq, double radius, int inclusive,

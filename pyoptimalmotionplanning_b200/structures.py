@@ -227,6 +227,17 @@ class NearestNeighbors(object):
         off, ids = self._be.neighbors(np.asarray([pt], dtype=np.float64), radius, self.inclusive_radius)
         return [(self._points[int(i)], self._datas[int(i)]) for i in ids]
 
+    def density(self, pt, radius, sigma):
+        """EST.density (kinodynamicplanner.py:688-693): sum of exp(-(d/sigma)^2) over the nodes within radius."""
+        if self._be is None or len(self) == 0:
+            return 0.0
+        self._sync_metric()
+        return float(self._be.density(np.asarray([pt], dtype=np.float64), radius, sigma, self.inclusive_radius)[0][0])
+
+    def density_batch(self, queries, radius, sigma):
+        self._sync_metric()
+        return self._be.density(queries, radius, sigma, self.inclusive_radius)
+
     # ------------------------------------------------------------------ batched extras
     def nearest_batch(self, queries):
         """(idx[nq], dist[nq]) for a batch of queries; idx = -1 where nothing is admissible."""

@@ -71,6 +71,9 @@ class OracleNN(object):
     def neighbors(self, q, radius, inclusive=True):
         return oracle.nn_neighbors(self.spec, self.pts, q, radius, inclusive, self._mask())
 
+    def density(self, q, radius, sigma, inclusive=True):
+        return oracle.nn_density(self.spec, self.pts, q, radius, sigma, inclusive, self._mask())
+
     def rewire_candidates(self, space, x, k, res):
         ids, dist, cnt = oracle.nn_knearest(self.spec, self.pts, [list(x)], k, self._mask())
         c = int(cnt[0])

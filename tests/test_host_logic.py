@@ -335,6 +335,28 @@ def test_unmodified_rrt_star_with_rewire_batch_matches_reference():
 
 
 @needs_ref
+def test_est_density_equals_reference_loop():
+    """EST.density (kinodynamicplanner.py:688-693) through NearestNeighbors.density of the drop-in."""
+    refshim.load()
+    import math
+    from pomp.structures.nearestneighbors import NearestNeighbors as RefNN
+    from pomp.spaces.metric import euclideanMetric
+    rng = random.Random(4)
+    pts = [[rng.random(), rng.random()] for _ in range(1500)]
+    ref = RefNN(euclideanMetric, "kdtree")
+    mine = fake_nn(euclideanMetric)
+    for i, p in enumerate(pts):
+        ref.add(p, i)
+        mine.add(p, i)
+    radius = 0.03
+    for _ in range(40):
+        x = [rng.random(), rng.random()]
+        want = sum(math.exp(-(euclideanMetric(nx, x) / radius) ** 2) for nx, n in ref.neighbors(x, radius * 4.0))
+        got = mine.density(x, radius * 4.0, radius)
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want))
+
+
+@needs_ref
 def test_edge_checker_dispatch_on_reference_interpolators():
     refshim.load()
     from pomp.spaces.edgechecker import EpsilonEdgeChecker as RefChecker
