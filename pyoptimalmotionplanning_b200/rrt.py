@@ -252,9 +252,18 @@ class RepeatedRRTForest(RRTForest):
         self.totalIters = [0] * self.T
 
     def planMore(self, iters):
+        """Per trial exactly RepeatedRRT.planMore(iters): a trial that reaches the goal RETURNS from this call
+        (kinodynamicplanner.py:1291-1312) -- here it sits out the rest of the call -- so under the reference
+        harness's planMore(10) loop (planners/test.py:24-40) trial t reproduces the single-trial run of its seed
+        iteration for iteration."""
+        live = [True] * self.T
         for _ in range(iters):
-            new = self.expand_all()
+            if not any(live):
+                break
+            new = self.expand_all(live)
             for t, n in enumerate(new):
+                if not live[t]:
+                    continue
                 self.numIters[t] += 1
                 self.totalIters[t] += 1
                 if n is None:
@@ -270,3 +279,40 @@ class RepeatedRRTForest(RRTForest):
                         path.reverse()
                         self.bestPath[t] = path
                     self.reset_trial(t)
+                    live[t] = False
+
+
+def testForest(forest, max_iters, filename, check_every=10, trial_offset=0):
+    """The lock-step counterpart of pomp.planners.test.testPlanner (pomp/planners/test.py:8-52): all trials of
+    `forest` (a RepeatedRRTForest) advance together for `max_iters` planner iterations, and the result file has
+    the reference's layout byte for byte -- header ``trial,plan iters,plan time,best cost``, one row per change of
+    a trial's best cost (sampled every `check_every` = 10 iterations, like the reference's planMore(10) loop), one
+    closing row per trial -- so processresults.py / viewsummary.py read GPU runs unchanged.  Rows are grouped by
+    trial, trials numbered from `trial_offset` (ranks of a multi-GPU run write disjoint trial ranges).  The time
+    column is the wall time of the lock-step run at that point; the closing row carries the total.  Returns the
+    rows as (trial, iters, time, cost) tuples."""
+    import time
+    T = forest.T
+    rows = [[] for _ in range(T)]
+    cur = [float("inf")] * T
+    t0 = time.time()
+    iters = 0
+    while iters < max_iters:
+        step = min(check_every, max_iters - iters)
+        forest.planMore(step)
+        iters += step
+        t1 = time.time()
+        for t in range(T):
+            c = forest.bestPathCost[t]
+            if c is not None and c != cur[t]:
+                cur[t] = c
+                rows[t].append((trial_offset + t, iters, t1 - t0, c))
+    total = time.time() - t0
+    out = []
+    with open(filename, "w") as f:
+        f.write("trial,plan iters,plan time,best cost\n")
+        for t in range(T):
+            for r in rows[t] + [(trial_offset + t, iters, total, cur[t])]:
+                f.write(str(r[0]) + "," + str(r[1]) + "," + str(r[2]) + "," + str(r[3]) + "\n")
+                out.append(r)
+    return out

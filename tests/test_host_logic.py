@@ -84,6 +84,28 @@ def test_forest_driver_trials_equal_single_trial_goldens():
     assert sorted(set(c[1] for c in cps if c[1] is not None), reverse=True) == [c[1] for c in want]
 
 
+def test_forest_results_csv_has_the_reference_layout(tmp_path):
+    """testForest writes pomp/planners/test.py's CSV (header, a row per cost change, a closing row per trial);
+    trial 0 under seed 0 reproduces the golden cost trace of the reference's r-rrt run."""
+    import csv
+    from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest, testForest
+    g1 = G.load("planners.json")["G1_rrrt_bugtrap_bruteforce"]
+    rf = RepeatedRRTForest(G.space_spec(g1["space"]), g1["start"], [0, 5], g1["goal"], g1["goal_radius"],
+                           max_step=0.15, resolution=0.01, _backends=(OracleForest, OracleSpace))
+    fn = str(tmp_path / "rrrt.csv")
+    rows = testForest(rf, 700, fn)
+    with open(fn) as f:
+        lines = f.read().splitlines()
+    assert lines[0] == "trial,plan iters,plan time,best cost"
+    parsed = list(csv.reader(lines[1:]))
+    assert all(len(r) == 4 for r in parsed) and len(parsed) == len(rows)
+    assert [int(r[0]) for r in parsed] == sorted(int(r[0]) for r in parsed)          # grouped by trial
+    t0 = [(int(r[1]), float(r[3])) for r in parsed if r[0] == "0"]
+    want = [(c[0], c[1]) for c in g1["change_points"] if c[0] <= 700]
+    assert t0[:-1] == want and t0[-1] == (700, want[-1][1])                           # closing row repeats the best
+    assert [r for r in parsed if r[0] == "1"][-1][1] == "700"
+
+
 def test_nearestneighbors_bookkeeping_without_reference():
     nn = fake_nn(P.MetricSpec.euclidean(2))
     assert nn.nearest([0, 0]) is None and nn.knearest([0, 0], 3) == [] and nn.neighbors([0, 0], 1) == []
