@@ -508,7 +508,7 @@ def run_gpu(args):
     q_slice_h = torch.from_numpy(q_all_h).pin_memory()
     pts = torch.from_numpy(pts_h).cuda(local)
     nn = CudaNN(MetricSpec.euclidean(DIM), local)
-    for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks"):
+    for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks", "use_graphs", "pipeline_shape"):
         if "POMP_" + name.upper() in os.environ:   # tuning experiments
             nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
     nn.set_device(pts.data_ptr(), n, st)
@@ -624,7 +624,7 @@ def run_gpu(args):
                              "traffic": measured_traffic("grid_knn_D2_k1")},
                 "e2e": {"value": world * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": qs * DIM * 8 * world,
                         "d2h_bytes_per_step": qs * K * 16 * world, "ms_per_step": e2e_s * 1e3,
-                        "api": "pomp_nn_nearest_h (pinned host buffers; H2D / search / D2H pipelined over 4 chunks)"},
+                        "api": "pomp_nn_nearest_h (pinned host buffers; H2D / search / D2H pipelined over chunks, chunk searches replayed as CUDA graphs)"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "index": {"cells": nn.get_stat("n_cells"), "overflow_queries_last_step": nn.get_stat("overflow_queries")}}
         if sharded is not None:

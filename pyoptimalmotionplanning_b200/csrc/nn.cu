@@ -819,6 +819,7 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   h->grid = g;
   h->grid_valid = true;
   h->grid_unusable = false;
+  h->grid_builds++;
   return POMP_OK;
 }
 
@@ -1283,6 +1284,8 @@ POMP_API int pomp_nn_destroy(pomp_nn* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
+  for (auto& cg : h->chunk_graphs)
+    if (cg.exec) cudaGraphExecDestroy(cg.exec);
   for (cudaEvent_t e : h->ovl_ev) cudaEventDestroy(e);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
@@ -1408,6 +1411,7 @@ POMP_API int pomp_nn_update_metric(pomp_nn* h, const pomp_metric_desc* metric) {
   bool same = (metric->kind == h->metric.kind) && (metric->has_cost == h->metric.has_cost);
   for (int i = 0; i < base_dim(*metric) && same; i++) same = (s0[i] == s1[i]);
   h->metric = *metric;
+  h->mut_count++;
   if (!same) {
     h->grid_valid = false;
     h->grid_unusable = false;
@@ -1416,6 +1420,7 @@ POMP_API int pomp_nn_update_metric(pomp_nn* h, const pomp_metric_desc* metric) {
 }
 
 POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
+  if (h) h->mut_count++;
   POMP_REQUIRE(h && name, "bad arguments to pomp_nn_set_param");
   std::string s(name);
   if (s == "grid_min_points") h->grid_min_points = value;
@@ -1431,6 +1436,8 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "pipe_search") h->pipe_search = value;
   else if (s == "two_stage") h->two_stage = value;
   else if (s == "block_need") h->block_need = value;
+  else if (s == "use_graphs") h->use_graphs = value;
+  else if (s == "pipeline_shape") h->pipeline_shape = value;
   else if (s == "periodic_axes") {
     h->periodic_axes = value;
     h->grid_valid = false;
@@ -1502,6 +1509,73 @@ POMP_API int pomp_nn_nearest(pomp_nn* h, const double* q, int64_t nq, int64_t* i
   return pomp_nn_knearest(h, q, nq, 1, idx, dist, nullptr, stream);
 }
 
+// everything a captured chunk search bakes into its kernel arguments
+static uint64_t launch_signature(const pomp_nn* h) {
+  uint64_t x = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) { x = (x ^ v) * 1099511628211ull; };
+  mix((uint64_t)h->n_dev);
+  mix((uint64_t)(uintptr_t)h->d_pts);
+  mix((uint64_t)(uintptr_t)h->skip_ptr());
+  mix(h->grid_builds);
+  mix(h->mut_count);
+  return x | 1ull;
+}
+
+// One chunk of the pipelined *_h path.  The second time the same chunk shape comes by under the same
+// launch signature its launches are captured into a CUDA graph; from then on the chunk is ONE graph
+// launch (the first, direct run has sized every scratch buffer, so nothing allocates while capturing).
+static int knn_chunk(pomp_nn* h, int c, const double* q, int64_t m, int k, int64_t* idx, double* dist, int32_t* cnt,
+                     cudaStream_t st) {
+  if (h->use_graphs == 0 || h->profile) return knn_device(h, q, m, k, idx, dist, cnt, st);
+  if ((int)h->chunk_graphs.size() <= c) h->chunk_graphs.resize((size_t)c + 1);
+  pomp_nn::ChunkGraph& G = h->chunk_graphs[c];
+  POMP_TRY(nn_flush(h, st));
+  bool use_grid = false;
+  POMP_TRY(want_grid(h, m, &use_grid, st));  // builds / refreshes the index outside any capture
+  const uint64_t sig = launch_signature(h);
+  const bool same_shape = G.q == q && G.m == m && G.k == k && G.idx == idx && G.dist == dist && G.cnt == cnt;
+  if (G.exec && same_shape && G.sig == sig) {
+    CUDA_TRY(cudaGraphLaunch(G.exec, st));
+    pomp::g_launches.fetch_add(G.launches, std::memory_order_relaxed);
+    return POMP_OK;
+  }
+  if (G.exec) {
+    cudaGraphExecDestroy(G.exec);
+    G.exec = nullptr;
+  }
+  if (same_shape && G.seen_sig == sig) {
+    const int64_t l0 = pomp::g_launches.load();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+    int rc = POMP_OK;
+    if (e == cudaSuccess) {
+      rc = knn_device(h, q, m, k, idx, dist, cnt, st);
+      e = cudaStreamEndCapture(st, &graph);
+    }
+    if (e == cudaSuccess && rc == POMP_OK && graph) e = cudaGraphInstantiate(&G.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc != POMP_OK || !G.exec) {
+      // capture refused: nothing ran; run the chunk directly and stop trying
+      (void)cudaGetLastError();
+      G.exec = nullptr;
+      h->use_graphs = 0;
+      return knn_device(h, q, m, k, idx, dist, cnt, st);
+    }
+    G.sig = sig;
+    G.launches = pomp::g_launches.load() - l0;
+    CUDA_TRY(cudaGraphLaunch(G.exec, st));
+    return POMP_OK;
+  }
+  G.q = q;
+  G.m = m;
+  G.k = k;
+  G.idx = idx;
+  G.dist = dist;
+  G.cnt = cnt;
+  G.seen_sig = sig;
+  return knn_device(h, q, m, k, idx, dist, cnt, st);
+}
+
 POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32_t k, int64_t* idx_h,
                                 double* dist_h, int32_t* count_h) {
   POMP_REQUIRE(h && (nq == 0 || (q_h && idx_h && dist_h)) && nq >= 0, "bad arguments to pomp_nn_knearest_h");
@@ -1536,19 +1610,37 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
     // chunk sizes shrink towards the end (weights nchunk+1, nchunk, ..., 2): the search and copy-out of
     // the LAST chunk cannot hide behind anything, so it is the smallest (host-to-device is the slower
     // direction on this box: 36 vs 56 GB/s, profiles/pcie_probe.py)
-    const int64_t wsum = (int64_t)nchunk * (nchunk + 3) / 2;
+    // pipeline_shape 1: triangle (small first chunk so that copy-out starts early, small last chunk)
+    std::vector<double> wts((size_t)nchunk);
+    double wtot = 0.0;
+    for (int c = 0; c < nchunk; c++) {
+      wts[c] = h->pipeline_shape != 0 ? (double)std::min(c + 1, nchunk - c) + 0.5 : (double)(nchunk + 1 - c);
+      wtot += wts[c];
+    }
     int64_t b = 0;
+    // POMP_PIPE_TRACE=1: per-chunk completion times of the three stages on stderr (debug aid)
+    static const bool trace = getenv("POMP_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+      tev.resize(1 + 3 * (size_t)nchunk);
+      for (auto& e : tev) CUDA_TRY(cudaEventCreate(&e));
+      CUDA_TRY(cudaEventRecord(tev[0], st));
+      CUDA_TRY(cudaStreamWaitEvent(h->copy_in, tev[0], 0));
+    }
+    int nc_done = 0;
     for (int c = 0; c < nchunk && b < nq; c++) {
-      int64_t m = (nq * (nchunk + 1 - c) / wsum + 127) / 128 * 128;
+      int64_t m = ((int64_t)((double)nq * wts[c] / wtot) + 127) / 128 * 128;
       if (c == nchunk - 1 || b + m > nq) m = nq - b;
       const int64_t e = b + m;
       CUDA_TRY(cudaMemcpyAsync(h->q_dev.p + b * h->D, q_h + b * h->D, sizeof(double) * (size_t)m * h->D,
                                cudaMemcpyHostToDevice, h->copy_in));
       CUDA_TRY(cudaEventRecord(h->pipe_ev[2 * c], h->copy_in));
+      if (trace) CUDA_TRY(cudaEventRecord(tev[1 + 3 * c], h->copy_in));
       CUDA_TRY(cudaStreamWaitEvent(st, h->pipe_ev[2 * c], 0));
-      POMP_TRY(knn_device(h, h->q_dev.p + b * h->D, m, k, h->out_idx.p + b * k, h->out_dist.p + b * k,
-                          count_h ? h->out_cnt.p + b : nullptr, st));
+      POMP_TRY(knn_chunk(h, c, h->q_dev.p + b * h->D, m, k, h->out_idx.p + b * k, h->out_dist.p + b * k,
+                         count_h ? h->out_cnt.p + b : nullptr, st));
       CUDA_TRY(cudaEventRecord(h->pipe_ev[2 * c + 1], st));
+      if (trace) CUDA_TRY(cudaEventRecord(tev[2 + 3 * c], st));
       CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->pipe_ev[2 * c + 1], 0));
       CUDA_TRY(cudaMemcpyAsync(idx_h + b * k, h->out_idx.p + b * k, sizeof(int64_t) * (size_t)m * k,
                                cudaMemcpyDeviceToHost, h->copy_out));
@@ -1557,10 +1649,22 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
       if (count_h)
         CUDA_TRY(cudaMemcpyAsync(count_h + b, h->out_cnt.p + b, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost,
                                  h->copy_out));
+      if (trace) CUDA_TRY(cudaEventRecord(tev[3 + 3 * c], h->copy_out));
+      nc_done = c + 1;
       b = e;
     }
     CUDA_TRY(cudaStreamSynchronize(h->copy_out));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (trace) {
+      for (int c = 0; c < nc_done; c++) {
+        float t1 = 0, t2 = 0, t3 = 0;
+        cudaEventElapsedTime(&t1, tev[0], tev[1 + 3 * c]);
+        cudaEventElapsedTime(&t2, tev[0], tev[2 + 3 * c]);
+        cudaEventElapsedTime(&t3, tev[0], tev[3 + 3 * c]);
+        fprintf(stderr, "pomp pipe chunk %d: h2d done %.3f  search done %.3f  d2h done %.3f ms\n", c, t1, t2, t3);
+      }
+      for (auto& e : tev) cudaEventDestroy(e);
+    }
     return POMP_OK;
   }
   CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, q_h, sizeof(double) * (size_t)nq * h->D, cudaMemcpyHostToDevice, st));

@@ -85,7 +85,23 @@ struct pomp_nn {
   cudaStream_t stream = nullptr;  // used by the *_h variants
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined *_h path
   std::vector<cudaEvent_t> pipe_ev;
-  double pipeline_chunks = 4;
+  double pipeline_chunks = 6;   // measured on B200 (2^20 2-D queries): 4: 0.575, 6: 0.552, 8: 0.567 ms end to end
+  double pipeline_shape = 1;    // chunk sizes: 0 = shrinking (C+1, C, ..., 2), 1 = triangle
+  // CUDA graphs of the per-chunk searches of the pipelined *_h path: with both copy engines busy every
+  // separate kernel launch costs ~8 us extra (profiles/chunk_probe.py), and a chunk is 8 small launches
+  struct ChunkGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t sig = 0;        // launch signature the graph was captured under
+    uint64_t seen_sig = 0;   // signature of the previous direct run with this shape
+    const double* q = nullptr;
+    int64_t m = 0;
+    int k = 0;
+    void *idx = nullptr, *dist = nullptr, *cnt = nullptr;
+    int64_t launches = 0;
+  };
+  std::vector<ChunkGraph> chunk_graphs;
+  double use_graphs = 1;
+  uint64_t grid_builds = 0, mut_count = 0;
   // optional timing of the dominant search kernel with CUDA events on the launching stream
   // (bench.py's roofline numerator); enabled with set_param("profile", 1)
   bool profile = false;

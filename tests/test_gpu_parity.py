@@ -475,3 +475,32 @@ def test_density_matches_oracle(name, grid):
     assert (np.abs(cnt.astype(int) - oc.astype(int)) <= (0 if name == "euclid2" else 1)).all()
     ok = cnt == oc
     np.testing.assert_allclose(dens[ok], od[ok], rtol=1e-12, atol=1e-300)
+
+
+def test_host_pipeline_graph_replay_sees_new_queries_and_new_points():
+    """The pipelined host-buffer path replays CUDA graphs of its chunk searches from the third call on: the
+    replays must read the NEW queries, and any change of the node set must drop the captured graphs."""
+    rng = np.random.default_rng(5)
+    m = MetricSpec.euclidean(2)
+    pts = rng.random((300000, 2))
+    nn = _nn(m, pts, grid=True)
+    nq = 140000      # >= 131072: pipelined over chunks
+    sub = rng.choice(nq, 800, replace=False)
+    for rep in range(4):
+        q = rng.random((nq, 2))
+        idx, dist = nn.nearest(q)
+        oi, od = oracle.nn_nearest(m, pts, q[sub])
+        assert (idx[sub] == oi).all() and (dist[sub] == od).all(), rep
+    extra = rng.random((50, 2))
+    nn.add(extra)
+    pts2 = np.concatenate([pts, extra])
+    for rep in range(3):
+        q = np.concatenate([extra + 1e-7, rng.random((nq - 50, 2))])
+        idx, dist = nn.nearest(q)
+        assert (idx[:50] == np.arange(300000, 300050)).all()
+        oi, od = oracle.nn_nearest(m, pts2, q[sub])
+        assert (idx[sub] == oi).all() and (dist[sub] == od).all(), rep
+    nn.remove(300010)
+    q = np.concatenate([extra + 1e-7, rng.random((nq - 50, 2))])
+    idx, dist = nn.nearest(q)
+    assert idx[10] != 300010 and (idx[:10] == np.arange(300000, 300010)).all()
