@@ -402,6 +402,18 @@ static int build_obstacle_grid(pomp_space* sp, const pomp_space_desc* d, cudaStr
   CUDA_TRY(cudaMalloc((void**)&sp->d_cell_items, sizeof(int) * items.size()));
   CUDA_TRY(cudaMemcpyAsync(sp->d_cell_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(sp->d_cell_items, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice, st));
+  std::vector<double> geom(items.size() * 4, 0.0);
+  for (size_t i = 0; i < items.size(); i++) {
+    const int o = items[i];
+    if (o < nb) {
+      for (int j = 0; j < 4; j++) geom[4 * i + j] = d->boxes_h[4 * (size_t)o + j];
+    } else {
+      for (int j = 0; j < 3; j++) geom[4 * i + j] = d->circles_h[3 * (size_t)(o - nb) + j];
+      geom[4 * i + 3] = NAN;
+    }
+  }
+  CUDA_TRY(cudaMalloc((void**)&sp->d_cell_geom, sizeof(double) * geom.size()));
+  CUDA_TRY(cudaMemcpyAsync(sp->d_cell_geom, geom.data(), sizeof(double) * geom.size(), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   s.use_grid = 1;
   s.gnx = gnx;
@@ -414,6 +426,7 @@ static int build_obstacle_grid(pomp_space* sp, const pomp_space_desc* d, cudaStr
   s.ginv1 = inv1;
   s.cell_start = sp->d_cell_start;
   s.cell_items = sp->d_cell_items;
+  s.cell_geom = sp->d_cell_geom;
   return POMP_OK;
 }
 
@@ -482,6 +495,7 @@ POMP_API int pomp_space_destroy(pomp_space* sp) {
   if (sp->d_circles) cudaFree(sp->d_circles);
   if (sp->d_cell_start) cudaFree(sp->d_cell_start);
   if (sp->d_cell_items) cudaFree(sp->d_cell_items);
+  if (sp->d_cell_geom) cudaFree(sp->d_cell_geom);
   if (sp->stream) cudaStreamDestroy(sp->stream);
   delete sp;
   return POMP_OK;

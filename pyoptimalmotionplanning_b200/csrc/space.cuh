@@ -22,6 +22,8 @@ struct SpaceDev {
   const double* circles;  // n_circles x 3
   const int* cell_start;  // gnx*gny + 1
   const int* cell_items;  // obstacle ids: boxes first, then n_boxes + circle id
+  const double* cell_geom;  // the same items with their geometry inline, 4 doubles each: box (x0,y0,x1,y1) or
+                            // circle (cx,cy,r,NaN) -- one dependent load less per candidate than id -> table
 };
 
 __host__ __device__ __forceinline__ int obs_cell(double x, double lo, double inv, int n) {
@@ -59,12 +61,15 @@ __device__ __forceinline__ bool hits_obstacle(const SpaceDev& s, double px, doub
   int cx = obs_cell(px, s.glo0, s.ginv0, s.gnx), cy = obs_cell(py, s.glo1, s.ginv1, s.gny);
   int c = cy * s.gnx + cx;
   int b = __ldg(s.cell_start + c), e = __ldg(s.cell_start + c + 1);
+  const double2* __restrict__ G = reinterpret_cast<const double2*>(s.cell_geom);
   for (int it = b; it < e; it++) {
-    int o = __ldg(s.cell_items + it);
-    if (o < s.n_boxes) {
-      if (in_box(s.boxes + 4 * o, px, py)) return true;
-    } else if (in_circle(s.circles + 3 * (o - s.n_boxes), px, py)) {
-      return true;
+    const double2 g0 = __ldg(G + 2 * it), g1 = __ldg(G + 2 * it + 1);
+    if (isnan(g1.y)) {  // circle (centre, radius): geometry.py:15-16
+      const double c[3] = {g0.x, g0.y, g1.x};
+      if (in_circle(c, px, py)) return true;
+    } else {
+      const double bx[4] = {g0.x, g0.y, g1.x, g1.y};
+      if (in_box(bx, px, py)) return true;
     }
   }
   return false;
@@ -93,6 +98,7 @@ struct pomp_space {
   double* d_circles = nullptr;
   int* d_cell_start = nullptr;
   int* d_cell_items = nullptr;
+  double* d_cell_geom = nullptr;
   cudaStream_t stream = nullptr;
   pomp::DevBuf<double> in_a, in_b;
   pomp::DevBuf<int32_t> in_i;
