@@ -124,7 +124,7 @@ def cpu_kdtree_run(steps, warmup, timed_as_main):
     Bounded sample: 2^CPU_LOG2_N points, 2^CPU_LOG2_Q queries per step."""
     from oracle import oracle
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = oracle.set_threads(cores)   # explicit: torchrun exports OMP_NUM_THREADS=1 to its ranks
     m = oracle.MetricSpec.euclidean(DIM)
     n, nq = 1 << CPU_LOG2_N, 1 << CPU_LOG2_Q
     pts = gen_points(1 << LOG2_N, DIM)[:n].copy()
@@ -508,7 +508,7 @@ def run_gpu(args):
     q_slice_h = torch.from_numpy(q_all_h).pin_memory()
     pts = torch.from_numpy(pts_h).cuda(local)
     nn = CudaNN(MetricSpec.euclidean(DIM), local)
-    for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks", "use_graphs", "pipeline_shape"):
+    for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks", "use_graphs", "pipeline_shape", "flat_u"):
         if "POMP_" + name.upper() in os.environ:   # tuning experiments
             nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
     nn.set_device(pts.data_ptr(), n, st)

@@ -240,3 +240,11 @@ def nn_density(metric_spec, pts, q, radius, sigma, inclusive=True, mask=None):
         dens[i] = d
         cnt[i] = off[i + 1] - off[i]
     return dens, cnt
+
+
+def set_threads(n):
+    """OpenMP threads used by the batched oracle loops; returns the count in effect."""
+    L = lib()
+    L.orc_set_threads.restype = C.c_int
+    L.orc_set_threads.argtypes = [C.c_int]
+    return int(L.orc_set_threads(int(n)))

@@ -19,6 +19,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/pomp_b200.h"
 
@@ -956,4 +959,16 @@ ORC_API void orc_rrt_extend(const pomp_metric_desc* m, const double* pts, int64_
     for (int j = 0; j < D; j++) xnew[j] = xrand[j];
   }
   *added = edge_linear(s, xn, xnew, res);
+}
+
+/* Thread count of the OpenMP loops (bench.py's CPU arm: torchrun exports OMP_NUM_THREADS=1, which would
+ * time the baseline on one core while reporting all of them).  Returns the count now in effect. */
+ORC_API int orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
 }

@@ -507,12 +507,11 @@ grid_knn_block_kernel(GridDev g, const double* __restrict__ pts, long long n, co
 // (U independent 16-byte loads in flight) -- fewer dependent memory round trips per thread and a
 // single loop whose trip count varies little across the warp.  Returns whether the result is
 // certified exact (same certificate as grid_knn_block_kernel).
-template <int K, int R, class L>
+template <int K, int R, class L, int U = 4>
 __device__ __forceinline__ bool flat2d_search(const GridDev& g, const double* __restrict__ pts, long long n,
                                               const uint8_t* __restrict__ skip, const double (&qq)[2], int cx,
                                               int cy, L& top) {
   constexpr int NR = 2 * R + 1;
-  constexpr int U = 4;
   const int W = g.ncell[0], H = g.ncell[1];
   const int x0 = max(cx - R, 0), x1 = min(cx + R, W - 1);
   int s[NR], pre[NR + 1];
@@ -782,8 +781,8 @@ __device__ __forceinline__ void warp_retry_nn2d(const GridDev& g, const double* 
   }
 }
 
-template <int K, int R, bool RETRY = true>
-__global__ void __launch_bounds__(128, (K <= 4 ? 8 : 4))  // 64 regs; 48 (10 blocks/SM) spills and measured slower
+template <int K, int R, bool RETRY = true, int U = 4>
+__global__ void __launch_bounds__(128, (K <= 4 ? (U <= 2 ? 10 : (U <= 4 ? 8 : (U <= 6 ? 6 : 5))) : 4))  // 64 regs at U = 4; 48 (10 blocks/SM) spills and measured slower
 grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
                        const double* __restrict__ q, const double* __restrict__ qs, long long nq,
                        const int* __restrict__ qperm, int k, int64_t* __restrict__ out_idx,
@@ -818,7 +817,7 @@ grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
       cy = grid_cell(g, 1, qq[1]);
       typename BestList<1>::type top;
       top.init(IdxResolver{g.sidx, g.n_indexed});
-      if (flat2d_search<1, R>(g, pts, n, skip, qq, cx, cy, top)) {
+      if (flat2d_search<1, R, typename BestList<1>::type, U>(g, pts, n, skip, qq, cx, cy, top)) {
         int idx[1];
         top.finish(idx);
         const bool fin = top.d[0] < POMP_INF;

@@ -1436,6 +1436,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "pipe_search") h->pipe_search = value;
   else if (s == "two_stage") h->two_stage = value;
   else if (s == "block_need") h->block_need = value;
+  else if (s == "flat_u") h->flat_u = value;
   else if (s == "use_graphs") h->use_graphs = value;
   else if (s == "pipeline_shape") h->pipeline_shape = value;
   else if (s == "periodic_axes") {

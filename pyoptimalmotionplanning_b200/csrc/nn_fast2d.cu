@@ -88,6 +88,19 @@ int pomp::launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsor
     prof_end(h, st);
     FLAT(1, 1, (blocks + 7) / 8, npd, np, l2, c2, (const int*)l1, (const int*)c1);
     PRUNED(1, l2, c2);
+  } else if (KK == 1 && R == 1 && !small_two && h->flat_u != 4) {
+    // experiment knob: candidate loads in flight per thread (registers vs round trips)
+    if (h->flat_u == 2)
+      LAUNCH((grid_knn_flat2d_kernel<1, 1, true, 2>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,
+             qsorted, (long long)nq, qperm, k, idx, dist, cnt, l1, c1, np, np);
+    else if (h->flat_u == 6)
+      LAUNCH((grid_knn_flat2d_kernel<1, 1, true, 6>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,
+             qsorted, (long long)nq, qperm, k, idx, dist, cnt, l1, c1, np, np);
+    else
+      LAUNCH((grid_knn_flat2d_kernel<1, 1, true, 8>), blocks, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q,
+             qsorted, (long long)nq, qperm, k, idx, dist, cnt, l1, c1, np, np);
+    prof_end(h, st);
+    PRUNED(1, l1, c1);
   } else if (KK == 1) GK(1);
   else if (KK == 4) GK(4);
   else if (KK == 8) GK(8);
