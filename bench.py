@@ -577,6 +577,23 @@ def run_gpu(args):
     e2e_s = float(t.item())
     # sanity: the e2e answers equal the device-resident answers
     assert torch.equal(idx_h[:, 0], idx.cpu()), "e2e result differs from the device-resident result"
+    # the reference's nearest() returns the node only: the same call without the distance array (extra, not the headline)
+    def e2e_idx_step():
+        check(nn.lib, nn.lib.pomp_nn_nearest_h(nn._h, C.c_void_p(q_slice_h.data_ptr()), qs,
+                                               C.c_void_p(idx_h.data_ptr()), C.c_void_p(0)))
+    for _ in range(3):
+        e2e_idx_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_idx_step()
+    barrier()
+    e2e_idx_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_idx_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_idx_s = float(t.item())
+    assert torch.equal(idx_h[:, 0], idx.cpu())
 
     # ---- N > 1 extra: the node-set-sharded path: rank r holds a DIFFERENT 2^24-point shard
     # (N x 2^24 points in total), the 2^20-query batch is split into per-rank slices, every step is
@@ -625,6 +642,9 @@ def run_gpu(args):
                 "e2e": {"value": world * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": qs * DIM * 8 * world,
                         "d2h_bytes_per_step": qs * K * 16 * world, "ms_per_step": e2e_s * 1e3,
                         "api": "pomp_nn_nearest_h (pinned host buffers; H2D / search / D2H pipelined over chunks, chunk searches replayed as CUDA graphs)"},
+                "e2e_index_only": {"value": world * nq / e2e_idx_s, "unit": "queries/s", "ms_per_step": e2e_idx_s * 1e3,
+                                   "d2h_bytes_per_step": qs * K * 8 * world,
+                                   "note": "same call with dist_h = NULL (NearestNeighbors.nearest returns the node only)"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "index": {"cells": nn.get_stat("n_cells"), "overflow_queries_last_step": nn.get_stat("overflow_queries")}}
         if sharded is not None:

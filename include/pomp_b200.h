@@ -120,7 +120,8 @@ int pomp_nn_get_stat(pomp_nn* h, const char* name, double* out);
 /* (re)build the uniform-grid bucket index over all points now (otherwise built lazily) */
 int pomp_nn_build_index(pomp_nn* h, void* stream);
 
-/* NearestNeighbors.nearest (:76-96): idx = -1 and dist = +inf when no admissible point exists */
+/* NearestNeighbors.nearest (:76-96): idx = -1 and dist = +inf when no admissible point exists.  The reference returns
+   the node only, so dist_h of the *_h variants may be NULL (the distances then stay on the device). */
 int pomp_nn_nearest(pomp_nn* h, const double* q, int64_t nq, int64_t* idx, double* dist, void* stream);
 int pomp_nn_nearest_h(pomp_nn* h, const double* q_h, int64_t nq, int64_t* idx_h, double* dist_h);
 /* NearestNeighbors.knearest (:98-116) + KNearestResult (knn.py:7-30): per query the k smallest

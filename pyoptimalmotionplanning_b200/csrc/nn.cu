@@ -1579,7 +1579,7 @@ static int knn_chunk(pomp_nn* h, int c, const double* q, int64_t m, int k, int64
 
 POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32_t k, int64_t* idx_h,
                                 double* dist_h, int32_t* count_h) {
-  POMP_REQUIRE(h && (nq == 0 || (q_h && idx_h && dist_h)) && nq >= 0, "bad arguments to pomp_nn_knearest_h");
+  POMP_REQUIRE(h && (nq == 0 || (q_h && idx_h)) && nq >= 0, "bad arguments to pomp_nn_knearest_h");  // dist_h may be NULL
   POMP_REQUIRE(k >= 1 && k <= 128, "k=%d outside 1..128", k);
   DeviceGuard g(h->device);
   if (!g.ok) return POMP_ERR_CUDA;
@@ -1645,8 +1645,9 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
       CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->pipe_ev[2 * c + 1], 0));
       CUDA_TRY(cudaMemcpyAsync(idx_h + b * k, h->out_idx.p + b * k, sizeof(int64_t) * (size_t)m * k,
                                cudaMemcpyDeviceToHost, h->copy_out));
-      CUDA_TRY(cudaMemcpyAsync(dist_h + b * k, h->out_dist.p + b * k, sizeof(double) * (size_t)m * k,
-                               cudaMemcpyDeviceToHost, h->copy_out));
+      if (dist_h)
+        CUDA_TRY(cudaMemcpyAsync(dist_h + b * k, h->out_dist.p + b * k, sizeof(double) * (size_t)m * k,
+                                 cudaMemcpyDeviceToHost, h->copy_out));
       if (count_h)
         CUDA_TRY(cudaMemcpyAsync(count_h + b, h->out_cnt.p + b, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost,
                                  h->copy_out));
@@ -1671,14 +1672,15 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
   CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, q_h, sizeof(double) * (size_t)nq * h->D, cudaMemcpyHostToDevice, st));
   POMP_TRY(knn_device(h, h->q_dev.p, nq, k, h->out_idx.p, h->out_dist.p, count_h ? h->out_cnt.p : nullptr, st));
   CUDA_TRY(cudaMemcpyAsync(idx_h, h->out_idx.p, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(dist_h, h->out_dist.p, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  if (dist_h)
+    CUDA_TRY(cudaMemcpyAsync(dist_h, h->out_dist.p, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
   if (count_h) CUDA_TRY(cudaMemcpyAsync(count_h, h->out_cnt.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return POMP_OK;
 }
 
 POMP_API int pomp_nn_nearest_h(pomp_nn* h, const double* q_h, int64_t nq, int64_t* idx_h, double* dist_h) {
-  POMP_REQUIRE(h && (nq == 0 || (q_h && idx_h && dist_h)) && nq >= 0, "bad arguments to pomp_nn_nearest_h");
+  POMP_REQUIRE(h && (nq == 0 || (q_h && idx_h)) && nq >= 0, "bad arguments to pomp_nn_nearest_h");  // dist_h may be NULL
   if (nq != 1) return pomp_nn_knearest_h(h, q_h, nq, 1, idx_h, dist_h, nullptr);
   // planner fast path: query travels in the kernel arguments, the answer lands in mapped host memory
   DeviceGuard g(h->device);
@@ -1688,7 +1690,7 @@ POMP_API int pomp_nn_nearest_h(pomp_nn* h, const double* q_h, int64_t nq, int64_
   const int64_t n = h->n_dev;
   if (n == 0) {
     *idx_h = -1;
-    *dist_h = INFINITY;
+    if (dist_h) *dist_h = INFINITY;
     return POMP_OK;
   }
   QueryArg qa;
@@ -1704,7 +1706,7 @@ POMP_API int pomp_nn_nearest_h(pomp_nn* h, const double* q_h, int64_t nq, int64_
   CUDA_TRY(cudaStreamSynchronize(st));
   const Mailbox* mb = (const Mailbox*)h->mailbox_h;
   *idx_h = mb->idx;
-  *dist_h = mb->dist;
+  if (dist_h) *dist_h = mb->dist;
   return POMP_OK;
 }
 
