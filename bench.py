@@ -479,6 +479,32 @@ def run_striped(world, rank, local, barrier):
     return out
 
 
+def pin_to_gpu_numa_node(local):
+    """One process per GPU: run this rank on the CPUs next to its GPU (sysfs local_cpulist of the PCI device), so
+    that the pinned host buffers it allocates afterwards are NUMA-local -- with 8 ranks the host<->device copies of
+    the e2e leg otherwise cross the socket interconnect.  Best effort; returns what it did."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"pci": bus, "cpus": len(cpus)}
+    except Exception as e:  # no sysfs / no permission: keep the default placement
+        return {"error": str(e)[:80]}
+    return None
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -493,6 +519,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peak, peak_src = peaks()
@@ -645,7 +672,7 @@ def run_gpu(args):
                 "e2e_index_only": {"value": world * nq / e2e_idx_s, "unit": "queries/s", "ms_per_step": e2e_idx_s * 1e3,
                                    "d2h_bytes_per_step": qs * K * 8 * world,
                                    "note": "same call with dist_h = NULL (NearestNeighbors.nearest returns the node only)"},
-                "gpu_launches": int(launches), "clocks": clocks,
+                "gpu_launches": int(launches), "clocks": clocks, "numa_pinning_rank0": numa,
                 "index": {"cells": nn.get_stat("n_cells"), "overflow_queries_last_step": nn.get_stat("overflow_queries")}}
         if sharded is not None:
             line["node_sharded"] = sharded
