@@ -400,32 +400,39 @@ __device__ __forceinline__ long long grid_cell_id(const GridDev& g, const double
   return id;
 }
 
+// Index build = counting sort of the points by cell id.  Scattering the POINTS (16-48 B each) to random
+// positions costs a read-modify-write of a DRAM sector per point (1.59 ms for 2^24 2-D points); instead
+// only the 4-byte insertion index is scattered, and the points are then GATHERED in sorted order
+// (random reads, coalesced writes).
 __global__ void cell_count_kernel(GridDev g, const double* __restrict__ pts, long long n, int D,
-                                  int* __restrict__ counts, int* __restrict__ slot) {
+                                  int* __restrict__ counts, int* __restrict__ slot, int* __restrict__ cellid) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double p[POMP_MAX_DIM];
   for (int j = 0; j < D; j++) p[j] = pts[i * D + j];
   long long c = grid_cell_id(g, p);
+  cellid[i] = (int)c;
   slot[i] = atomicAdd(counts + c, 1);
 }
-
-__global__ void cell_scatter_kernel(GridDev g, const double* __restrict__ pts, long long n, int D,
-                                    const int* __restrict__ cell_start, const int* __restrict__ slot,
-                                    double* __restrict__ spts, int* __restrict__ sidx) {
+__global__ void cell_scatter_kernel(long long n, const int* __restrict__ cell_start, const int* __restrict__ slot,
+                                    const int* __restrict__ cellid, int* __restrict__ sidx) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double p[POMP_MAX_DIM];
-  for (int j = 0; j < D; j++) p[j] = pts[i * D + j];
-  long long c = grid_cell_id(g, p);
-  long long pos = (long long)cell_start[c] + slot[i];
-  for (int j = 0; j < D; j++) spts[pos * D + j] = p[j];
-  sidx[pos] = (int)i;
+  sidx[(long long)cell_start[cellid[i]] + slot[i]] = (int)i;
 }
-
-// query ordering by COARSE home bin: bin = (cell row id) * nbx + (axis-0 cell >> shift).  Coarse bins
-// keep the locality (queries of one bin touch the same few KB of sorted points) while the histogram
-// and its scan stay tiny (tens of thousands of bins instead of millions of cells).
+template <int D>
+__global__ void cell_gather_kernel(const double* __restrict__ pts, long long n, int Drt,
+                                   const int* __restrict__ sidx, double* __restrict__ spts) {
+  long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  const long long i = sidx[pos];
+  if (D == 2) {
+    reinterpret_cast<double2*>(spts)[pos] = __ldg(reinterpret_cast<const double2*>(pts) + i);
+  } else {
+    const int dim = D ? D : Drt;
+    for (int j = 0; j < dim; j++) spts[pos * dim + j] = __ldg(pts + i * dim + j);
+  }
+}
 __global__ void query_cell_kernel(GridDev g, const double* __restrict__ q, long long nq, int D, int shift, int nbx,
                                   int row_div,
                                   int* __restrict__ counts, int* __restrict__ qcell, int* __restrict__ slot,
@@ -800,18 +807,20 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   g.n_indexed = (int)n;
   // counting sort of the points by cell id
   POMP_TRY(h->cell_start.reserve((size_t)total + 1 + 512));  // slack: the TMA path copies fixed-width slices
-  POMP_TRY(h->tmp_i32.reserve((size_t)n + (size_t)total));
+  POMP_TRY(h->tmp_i32.reserve((size_t)2 * n + (size_t)total));
   POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(total)));
   POMP_TRY(h->spts.reserve((size_t)n * D));
   POMP_TRY(h->sidx.reserve((size_t)n));
   int* slot = h->tmp_i32.p;
-  int* counts = h->tmp_i32.p + n;
+  int* cellid = h->tmp_i32.p + n;
+  int* counts = h->tmp_i32.p + 2 * n;
   CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)total, st));
   int blocks = (int)((n + 255) / 256);
-  LAUNCH(cell_count_kernel, blocks, 256, 0, st, g, h->d_pts, (long long)n, D, counts, slot);
+  LAUNCH(cell_count_kernel, blocks, 256, 0, st, g, h->d_pts, (long long)n, D, counts, slot, cellid);
   POMP_TRY(exclusive_scan<int>(counts, total, h->cell_start.p, h->scan_tmp.p, st));
-  LAUNCH(cell_scatter_kernel, blocks, 256, 0, st, g, h->d_pts, (long long)n, D, h->cell_start.p, slot, h->spts.p,
-         h->sidx.p);
+  LAUNCH(cell_scatter_kernel, blocks, 256, 0, st, (long long)n, h->cell_start.p, slot, cellid, h->sidx.p);
+  if (D == 2) LAUNCH((cell_gather_kernel<2>), blocks, 256, 0, st, h->d_pts, (long long)n, D, h->sidx.p, h->spts.p);
+  else LAUNCH((cell_gather_kernel<0>), blocks, 256, 0, st, h->d_pts, (long long)n, D, h->sidx.p, h->spts.p);
   CHECK_LAUNCH();
   g.cell_start = h->cell_start.p;
   g.spts = h->spts.p;
