@@ -239,6 +239,13 @@ def run_extras(peak):
         out["edge_checks_kink10k_res%g" % res] = {"edges_per_s": ne / ms * 1e3, "ms": ms,
                                                   "hbm_frac": ne * 33 / (ms * 1e-3) / 1e9 / peak,
                                                   "feasible_frac": float(ok.float().mean().item())}
+    # point feasibility (a7): the 4 Mi roadmap samples against the same obstacle field
+    okp = torch.empty(ne, dtype=torch.uint8, device="cuda")
+    ms = time_cuda(lambda: space.feasible_device(a.data_ptr(), ne, okp.data_ptr(), st), reps=5, warm=2)
+    out["feasible_points_kink10k"] = {"points_per_s": ne / ms * 1e3, "ms": ms,
+                                      "hbm_frac": ne * 17 / (ms * 1e-3) / 1e9 / peak,
+                                      "feasible_frac": float(okp.float().mean().item())}
+    del okp
     # edge set A: every roadmap sample -> its 8 nearest neighbours, as (i, j) index pairs into the
     # sample array (the k-NN kernel builds the edge list: k = 9, the first hit is the sample itself)
     nodes = a
