@@ -840,6 +840,70 @@ grid_knn_flat2d_kernel(GridDev g, const double* __restrict__ pts, long long n, c
   flat2d_one<K, R, RETRY>(g, pts, n, skip, qq, qi, k, out_idx, out_dist, out_cnt, ovf_list, ovf_count);
 }
 
+// Radius queries in ONE traversal: the count pass also parks the (unresolved) positions of up to
+// RADIUS_STAGE_CAP hits per query in a staging buffer; after the scan of the counts a warp per query
+// resolves them to insertion indices, sorts them (shuffle bitonic network) and writes its CSR segment
+// with coalesced stores.  Only queries with more hits than that are traversed a second time.
+constexpr int RADIUS_STAGE_CAP = 32;
+
+struct RadiusStage {
+  double radius, tsq;
+  int inclusive;
+  int cnt;
+  int* stage;  // this query's RADIUS_STAGE_CAP slots
+  __device__ __forceinline__ double threshold() const { return radius; }
+  __device__ __forceinline__ double tsq_up() const { return tsq; }
+  __device__ __forceinline__ void offer_sq(double s, int pos) {
+    if (!(s <= tsq)) return;
+    double d = sqrt(s);
+    bool hit = inclusive ? (d <= radius) : (d < radius);
+    if (hit) {
+      if (cnt < RADIUS_STAGE_CAP) stage[cnt] = pos;
+      cnt++;
+    }
+  }
+};
+
+template <int D>
+__global__ void __launch_bounds__(128)
+grid_radius_stage_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                         const double* __restrict__ q, long long nq, double radius, int inclusive,
+                         int* __restrict__ counts, int* __restrict__ stage, int* __restrict__ n_long) {
+  long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  double qq[D];
+  load_point<D>(q, qi, qq);
+  RadiusStage c{radius, tsq_of(radius), inclusive, 0, stage + qi * RADIUS_STAGE_CAP};
+  double gap[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) gap[i] = 0.0;
+  FastLevel<D, D - 1>::run(g, skip, qq, gap, 0LL, c, 0, 0);
+  scan_tail<D>(g, pts, n, skip, qq, c);
+  counts[qi] = c.cnt;
+  if (c.cnt > RADIUS_STAGE_CAP) atomicAdd(n_long, 1);
+}
+
+static __global__ void __launch_bounds__(256)
+radius_finalize_kernel(const int* __restrict__ counts, const int64_t* __restrict__ offsets,
+                       const int* __restrict__ stage, IdxResolver res, long long nq, int64_t* __restrict__ out) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nq) return;
+  const int len = counts[w];
+  if (len == 0 || len > RADIUS_STAGE_CAP) return;
+  long long v = lane < len ? (long long)res(stage[w * RADIUS_STAGE_CAP + lane]) : 0x7fffffffffffffffLL;
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const long long o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+      v = (lower == up) ? (v < o ? v : o) : (v > o ? v : o);
+    }
+  }
+  if (lane < len) out[offsets[w] + lane] = v;
+}
+
 template <int D, bool FILL>
 __global__ void __launch_bounds__(128)
 grid_radius_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
@@ -847,6 +911,7 @@ grid_radius_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, 
                         int* __restrict__ counts, const int64_t* __restrict__ offsets, int64_t* __restrict__ out) {
   long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= nq) return;
+  if (FILL && counts && counts[qi] <= RADIUS_STAGE_CAP) return;  // finished from the staging buffer already
   double qq[D];
   load_point<D>(q, qi, qq);
   RadiusFast<FILL> c{radius, tsq_of(radius), inclusive, 0, IdxResolver{g.sidx, g.n_indexed},
@@ -856,8 +921,76 @@ grid_radius_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, 
   for (int i = 0; i < D; i++) gap[i] = 0.0;
   FastLevel<D, D - 1>::run(g, skip, qq, gap, 0LL, c, 0, 0);
   scan_tail<D>(g, pts, n, skip, qq, c);
-  if (FILL) heapsort_i64(out + offsets[qi], c.cnt);
-  else counts[qi] = (int)c.cnt;
+  if (FILL) {
+    if (c.cnt > 32) heapsort_i64(out + offsets[qi], c.cnt);  // short segments: segment_sort32_kernel, warp-wide
+  } else {
+    counts[qi] = (int)c.cnt;
+  }
+}
+
+// Hits of a radius query are reported in insertion-index order.  One warp per query sorts a segment of
+// up to 32 hits with a shuffle bitonic network (coalesced load, 15 compare-exchange stages, coalesced
+// store); longer segments were heap-sorted by the thread that produced them.  (A per-thread heap sort in
+// global memory for every query made the fill pass 4x as long as the count pass.)
+static __global__ void __launch_bounds__(256)
+segment_sort32_kernel(const int64_t* __restrict__ offsets, int64_t* __restrict__ vals, long long nq) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nq) return;
+  const int64_t b = offsets[w];
+  const long long len = offsets[w + 1] - b;
+  if (len < 2 || len > 32) return;
+  long long v = lane < len ? vals[b + lane] : 0x7fffffffffffffffLL;
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const long long o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+      v = (lower == up) ? (v < o ? v : o) : (v > o ? v : o);
+    }
+  }
+  if (lane < len) vals[b + lane] = v;
+}
+
+// EST Gaussian density for the plain Euclidean metric: the radius traversal with the hits folded into
+// sum exp(-(d/sigma)^2) (kinodynamicplanner.py:688-693)
+struct DensityFast {
+  double radius, tsq, inv_sigma;
+  int inclusive;
+  double sum;
+  int cnt;
+  __device__ __forceinline__ double threshold() const { return radius; }
+  __device__ __forceinline__ double tsq_up() const { return tsq; }
+  __device__ __forceinline__ void offer_sq(double s, int) {
+    if (!(s <= tsq)) return;
+    double d = sqrt(s);
+    bool hit = inclusive ? (d <= radius) : (d < radius);
+    if (hit) {
+      double t = d * inv_sigma;
+      sum += exp(-(t * t));
+      cnt++;
+    }
+  }
+};
+
+template <int D>
+__global__ void __launch_bounds__(128)
+grid_density_fast_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
+                         const double* __restrict__ q, long long nq, double radius, double sigma, int inclusive,
+                         double* __restrict__ dens, int32_t* __restrict__ cnt) {
+  long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  double qq[D];
+  load_point<D>(q, qi, qq);
+  DensityFast c{radius, tsq_of(radius), 1.0 / sigma, inclusive, 0.0, 0};
+  double gap[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) gap[i] = 0.0;
+  FastLevel<D, D - 1>::run(g, skip, qq, gap, 0LL, c, 0, 0);
+  scan_tail<D>(g, pts, n, skip, qq, c);
+  dens[qi] = c.sum;
+  if (cnt) cnt[qi] = c.cnt;
 }
 
 }  // namespace pomp

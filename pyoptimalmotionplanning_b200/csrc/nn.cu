@@ -588,8 +588,11 @@ grid_radius_kernel(GridDev g, pomp_metric_desc m, const double* __restrict__ pts
     for (int j = 0; j < dim; j++) p[j] = __ldg(pts + i * dim + j);
     coll.offer_idx((D && EUCLID) ? euclid_fixed<DA>(p, qq) : metric_eval(m, p, qq), i);
   }
-  if (FILL) heapsort_i64(out + offsets[qi], coll.cnt);
-  else counts[qi] = (int)coll.cnt;
+  if (FILL) {
+    if (coll.cnt > 32) heapsort_i64(out + offsets[qi], coll.cnt);  // short segments: segment_sort32_kernel
+  } else {
+    counts[qi] = (int)coll.cnt;
+  }
 }
 
 // ---- Gaussian kernel density (EST): sum over the points within `radius` of exp(-(d/sigma)^2) ------
@@ -1192,6 +1195,42 @@ static int radius_device(pomp_nn* h, const double* q, int64_t nq, double radius,
   const int64_t n = h->n_dev;
   const uint8_t* skip = h->skip_ptr();
   int64_t total = 0;
+  if (use_grid && is_plain_euclid(h->metric) && h->grid.G == h->D && nq <= (int64_t)4 << 20 &&
+      (h->D == 2 || h->D == 3 || h->D == 4 || h->D == 6)) {
+    // one traversal: count + stage, scan, warp-per-query finalize; a second traversal only for the
+    // queries with more than RADIUS_STAGE_CAP hits
+    POMP_TRY(h->counts.reserve((size_t)nq + 2));
+    POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(nq)));
+    POMP_TRY(h->rstage.reserve((size_t)nq * RADIUS_STAGE_CAP));
+    int* n_long = h->counts.p + nq + 1;
+    CUDA_TRY(cudaMemsetAsync(n_long, 0, sizeof(int), st));
+    const int sb = (int)((nq + 127) / 128);
+#define RS(DD)                                                                                                       \
+  LAUNCH((grid_radius_stage_kernel<DD>), sb, 128, 0, st, h->grid, h->d_pts, (long long)n, skip, q, (long long)nq, radius, \
+         inclusive, h->counts.p, h->rstage.p, n_long)
+    if (h->D == 2) RS(2);
+    else if (h->D == 3) RS(3);
+    else if (h->D == 4) RS(4);
+    else RS(6);
+#undef RS
+    POMP_TRY(exclusive_scan<int64_t>(h->counts.p, nq, offsets, h->scan_tmp.p, st));
+    int nl = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, offsets + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&nl, n_long, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (needed_h) *needed_h = total;
+    if (total > idx_capacity) {
+      set_error("radius query produced %lld hits, capacity %lld", (long long)total, (long long)idx_capacity);
+      return POMP_ERR_CAPACITY;
+    }
+    if (total > 0) {
+      LAUNCH(radius_finalize_kernel, (int)((nq * 32 + 255) / 256), 256, 0, st, h->counts.p, offsets, h->rstage.p,
+             IdxResolver{h->grid.sidx, h->grid.n_indexed}, (long long)nq, idx);
+      if (nl > 0) POMP_TRY(grid_radius(h, true, q, nq, radius, inclusive, h->counts.p, offsets, idx, st));
+      CHECK_LAUNCH();
+    }
+    return POMP_OK;
+  }
   if (use_grid) {
     POMP_TRY(h->counts.reserve((size_t)nq + 1));
     POMP_TRY(h->scan_tmp.reserve(scan_scratch_elems(nq)));
@@ -1204,7 +1243,11 @@ static int radius_device(pomp_nn* h, const double* q, int64_t nq, double radius,
       set_error("radius query produced %lld hits, capacity %lld", (long long)total, (long long)idx_capacity);
       return POMP_ERR_CAPACITY;
     }
-    if (total > 0) POMP_TRY(grid_radius(h, true, q, nq, radius, inclusive, nullptr, offsets, idx, st));
+    if (total > 0) {
+      POMP_TRY(grid_radius(h, true, q, nq, radius, inclusive, nullptr, offsets, idx, st));
+      LAUNCH(segment_sort32_kernel, (int)((nq * 32 + 255) / 256), 256, 0, st, offsets, idx, (long long)nq);
+      CHECK_LAUNCH();
+    }
     return POMP_OK;
   }
   SplitGeom sg = split_geom(h, nq, n);
@@ -1242,13 +1285,23 @@ static int density_device(pomp_nn* h, const double* q, int64_t nq, double radius
   bool use_grid = false;
   POMP_TRY(want_grid(h, nq, &use_grid, st));
   const uint8_t* skip = h->skip_ptr();
-  if (use_grid) {
-    LAUNCH(grid_density_kernel, (int)((nq + 127) / 128), 128, 0, st, h->grid, h->metric, h->d_pts, (long long)h->n_dev,
+  const bool fastm = is_plain_euclid(h->metric) && h->grid.G == h->D;
+  const int db = (int)((nq + 127) / 128);
+#define DF(DD)                                                                                                   \
+  LAUNCH((grid_density_fast_kernel<DD>), db, 128, 0, st, h->grid, h->d_pts, (long long)h->n_dev, skip, q, (long long)nq, \
+         radius, sigma, inclusive, dens, cnt)
+  if (use_grid && fastm && h->D == 2) DF(2);
+  else if (use_grid && fastm && h->D == 3) DF(3);
+  else if (use_grid && fastm && h->D == 4) DF(4);
+  else if (use_grid && fastm && h->D == 6) DF(6);
+  else if (use_grid) {
+    LAUNCH(grid_density_kernel, db, 128, 0, st, h->grid, h->metric, h->d_pts, (long long)h->n_dev,
            skip, q, (long long)nq, radius, sigma, inclusive, dens, cnt);
   } else {
     LAUNCH(bf_density_kernel, (int)((nq * 32 + 255) / 256), 256, 0, st, h->d_pts, (long long)h->n_dev, h->metric, skip, q,
            (long long)nq, radius, sigma, inclusive, dens, cnt);
   }
+#undef DF
   CHECK_LAUNCH();
   return POMP_OK;
 }

@@ -77,6 +77,7 @@ struct pomp_nn {
   DevBuf<double> out_dist;
   DevBuf<int32_t> out_cnt;
   DevBuf<int64_t> out_off;
+  DevBuf<int> rstage;       // radius queries: parked hit positions, RADIUS_STAGE_CAP per query
   DevBuf<double> rw_ab;     // pomp_rewire_candidates_h: the 2k edges (a then b)
   DevBuf<uint8_t> rw_ok;
   // pinned mailbox for the single-query fast path
