@@ -227,6 +227,28 @@ def run_extras(peak):
             del off, hits, dens
         del nn, pts, q
         torch.cuda.empty_cache()
+    # planner regime: small node sets are searched by the brute-force warp kernels, bound by the FP64 pipe
+    # without FMA (one rounding per operation, like the reference): Q*N*(3D+2) separate DP operations per batch
+    import ctypes as C
+    lib = _abi.load_library()
+    fl = C.c_double()
+    _abi.check(lib, lib.pomp_fp64_unfused_peak(0, C.byref(fl)))
+    nb_n, nb_q = 1 << 16, 1 << 13
+    bp = torch.from_numpy(gen_points(nb_n, 2)).cuda()
+    bq = torch.from_numpy(gen_queries(nb_q, 2)).cuda()
+    bnn = CudaNN(MetricSpec.euclidean(2), 0)
+    bnn.set_param("grid_min_points", 1e18)   # force the brute-force regime
+    if "POMP_BF_TILED" in os.environ:
+        bnn.set_param("bf_tiled", float(os.environ["POMP_BF_TILED"]))
+    bnn.set_device(bp.data_ptr(), nb_n, st)
+    bi = torch.empty((nb_q, 1), dtype=torch.int64, device="cuda")
+    bd = torch.empty((nb_q, 1), dtype=torch.float64, device="cuda")
+    ms = time_cuda(lambda: bnn.knearest_device(bq.data_ptr(), nb_q, 1, bi.data_ptr(), bd.data_ptr(), None, st), reps=5, warm=2)
+    ops = nb_q * nb_n * (3 * 2 + 2)
+    out["bruteforce_nearest_N65536_Q8192"] = {"queries_per_s": nb_q / ms * 1e3, "ms": ms, "pairs_per_s": nb_q * nb_n / ms * 1e3,
+                                              "fp64_ops_per_s": ops / ms * 1e3, "fp64_unfused_peak_ops_per_s": fl.value,
+                                              "frac_of_unfused_fp64_peak": ops / (ms * 1e-3) / fl.value}
+    del bnn, bp, bq, bi, bd
     # Kink roadmap edge checks: 4 Mi samples, Kink's 4 boxes + 9996 small boxes, RRT-style edges <= 0.15
     sp = kink10k_space_spec()
     space = CudaSpace(sp, 0)

@@ -90,6 +90,9 @@ int pomp_version(void);
 int pomp_device_count(void);
 /* kernels launched by this library in this process so far (bench.py's gpu_launches) */
 int64_t pomp_launch_count(void);
+/* diagnostics: sustained FP64 operations/s of separate DADD/DMUL (no FMA) on `device` -- the roofline of the
+   brute-force kernels, which must round after every operation like the reference (pomp/klampt/vectorops.py:94-102) */
+int pomp_fp64_unfused_peak(int device, double* flops_out);
 
 /* NearestNeighbors.__init__ (nearestneighbors.py:14-23) */
 int pomp_nn_create(const pomp_metric_desc* metric, int64_t capacity_hint, int device, pomp_nn** out);

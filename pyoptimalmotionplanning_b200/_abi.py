@@ -65,6 +65,7 @@ SIGNATURES = {
     "pomp_version": (C.c_int, []),
     "pomp_device_count": (C.c_int, []),
     "pomp_launch_count": (_I64, []),
+    "pomp_fp64_unfused_peak": (C.c_int, [C.c_int, _P]),
     "pomp_nn_create": (C.c_int, [_MD, _I64, C.c_int, C.POINTER(_P)]),
     "pomp_nn_destroy": (C.c_int, [_P]),
     "pomp_nn_reset": (C.c_int, [_P]),

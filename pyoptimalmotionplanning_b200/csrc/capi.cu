@@ -58,3 +58,60 @@ POMP_API int pomp_device_count(void) {
   return n;
 }
 POMP_API int64_t pomp_launch_count(void) { return pomp::g_launches.load(); }
+
+// ---- diagnostics: un-fused FP64 throughput ---------------------------------------------------
+// The brute-force kernels of the planner regime (N <= ~1e5) are bound by the FP64 pipe WITHOUT
+// fused multiply-add (the reference rounds after every operation, so the library is compiled with
+// -fmad=false): Q*N*(3D+2) separate DADD/DMUL per batch.  This measures what the device sustains on
+// exactly that instruction mix -- the denominator bench.py reports the brute-force regime against
+// (SURVEY 8d), instead of the DFMA peak or HBM.
+namespace pomp {
+__global__ void __launch_bounds__(256) fp64_unfused_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.125, a2 = a0 + 0.25, a3 = a0 + 0.375;
+  double b0 = 1.0000001, b1 = 0.9999999, b2 = 1.0000002, b3 = 0.9999998;
+  const double c = 1e-9;
+  for (int i = 0; i < iters; i++) {  // 8 independent chains x (1 DMUL + 1 DADD): 16 FP64 ops per iteration
+    a0 = a0 * b0;
+    a1 = a1 * b1;
+    a2 = a2 * b2;
+    a3 = a3 * b3;
+    b0 = b0 + c;
+    b1 = b1 - c;
+    b2 = b2 + c;
+    b3 = b3 - c;
+    a0 = a0 + c;
+    a1 = a1 - c;
+    a2 = a2 + c;
+    a3 = a3 - c;
+    b0 = b0 * 0.99999999;
+    b1 = b1 * 1.00000001;
+    b2 = b2 * 0.99999999;
+    b3 = b3 * 1.00000001;
+  }
+  out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((b0 + b1) + (b2 + b3));
+}
+}  // namespace pomp
+
+POMP_API int pomp_fp64_unfused_peak(int device, double* flops_out) {
+  POMP_REQUIRE(flops_out != nullptr, "flops_out is NULL");
+  pomp::DeviceGuard g(device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  const int blocks = pomp::sm_count(device) * 8, threads = 256, iters = 20000;
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  LAUNCH(pomp::fp64_unfused_kernel, blocks, threads, 0, 0, d, 1000);  // warm-up
+  CUDA_TRY(cudaEventRecord(e0, 0));
+  LAUNCH(pomp::fp64_unfused_kernel, blocks, threads, 0, 0, d, iters);
+  CUDA_TRY(cudaEventRecord(e1, 0));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *flops_out = 16.0 * iters * (double)blocks * threads / (ms * 1e-3);
+  return POMP_OK;
+}

@@ -504,3 +504,25 @@ def test_host_pipeline_graph_replay_sees_new_queries_and_new_points():
     q = np.concatenate([extra + 1e-7, rng.random((nq - 50, 2))])
     idx, dist = nn.nearest(q)
     assert idx[10] != 300010 and (idx[:10] == np.arange(300000, 300010)).all()
+
+
+@pytest.mark.parametrize("D", [2, 3, 4, 6])
+def test_bruteforce_tiled_nearest_matches_oracle(D):
+    """Planner regime (no grid): query batches go through the shared-memory tiled kernel; exact ties (lattice
+    points), masks and ragged sizes must give the reference's answer (first minimum in insertion order)."""
+    rng = np.random.default_rng(40 + D)
+    m = MetricSpec.euclidean(D)
+    for n, nq, lattice in ((5000, 1500, False), (7777, 3001, True), (300, 1024, True)):
+        pts = rng.integers(0, 6, (n, D)).astype(np.float64) * 0.25 if lattice else rng.random((n, D))
+        q = rng.integers(0, 6, (nq, D)).astype(np.float64) * 0.25 + 0.125 if lattice else rng.random((nq, D))
+        for tiled in (1, 0):
+            nn = _nn(m, pts, grid=False)
+            nn.set_param("bf_tiled", tiled)
+            idx, dist = nn.nearest(q)
+            oi, od = oracle.nn_nearest(m, pts, q)
+            assert (idx == oi).all() and (dist == od).all(), (n, nq, lattice, tiled)
+            mask = (rng.random(n) < 0.5).astype(np.uint8)
+            nn.set_mask(mask)
+            idx, dist = nn.nearest(q)
+            oi, od = oracle.nn_nearest(m, pts, q, mask)
+            assert (idx == oi).all() and (dist == od).all(), (n, nq, lattice, tiled, "masked")
