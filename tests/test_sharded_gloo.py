@@ -85,3 +85,55 @@ def test_stripe_covers_everything():
             spans = [stripe(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def _stripe_worker(rank, world, port, out_dir):
+    """Edges and lock-step planner trials are independent units: every rank takes its stripe, no data-path
+    collective; the only communication is the final gather of the results (here: files + a barrier)."""
+    import random
+    from pyoptimalmotionplanning_b200 import SpaceSpec
+    from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest
+    from tests.fake_backend import OracleForest, OracleSpace
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sp = SpaceSpec([0, 0], [1, 1], boxes=[[0.3, 0.3, 0.7, 0.7]])
+    rng = np.random.default_rng(3)
+    a, b = rng.random((500, 2)), rng.random((500, 2))
+    e0, e1 = stripe(500, rank, world)
+    ok = oracle.edge_check(sp, a[e0:e1], b[e0:e1], 0.01)
+    flags = [None] * world
+    dist.all_gather_object(flags, (e0, np.asarray(ok, bool)))
+    if rank == 0:
+        full = np.concatenate([f[1] for f in sorted(flags, key=lambda t: t[0])])
+        np.save(os.path.join(out_dir, "edges.npy"), full)
+    t0, t1 = stripe(5, rank, world)
+    rf = RepeatedRRTForest(sp, [0.1, 0.5], list(range(t0, t1)), [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01,
+                           _backends=(OracleForest, OracleSpace))
+    for _ in range(30):
+        rf.planMore(10)
+    costs = [None] * world
+    dist.all_gather_object(costs, (t0, rf.bestPathCost))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "costs.npy"),
+                np.array([c if c is not None else np.inf for _, cs in sorted(costs) for c in cs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_striped_edges_and_trials_equal_single_process(tmp_path):
+    from pyoptimalmotionplanning_b200 import SpaceSpec
+    from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest
+    from tests.fake_backend import OracleForest, OracleSpace
+    port = _free_port()
+    mp.spawn(_stripe_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sp = SpaceSpec([0, 0], [1, 1], boxes=[[0.3, 0.3, 0.7, 0.7]])
+    rng = np.random.default_rng(3)
+    a, b = rng.random((500, 2)), rng.random((500, 2))
+    assert (np.load(tmp_path / "edges.npy") == np.asarray(oracle.edge_check(sp, a, b, 0.01), bool)).all()
+    rf = RepeatedRRTForest(sp, [0.1, 0.5], list(range(5)), [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01,
+                           _backends=(OracleForest, OracleSpace))
+    for _ in range(30):
+        rf.planMore(10)
+    want = np.array([c if c is not None else np.inf for c in rf.bestPathCost])
+    assert (np.load(tmp_path / "costs.npy") == want).all()      # trial t depends on seed t only, not on the striping
