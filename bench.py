@@ -403,7 +403,7 @@ def run_extras(peak):
                                  "us_batched": t_batch * 1e6, "us_one_call_per_edge": t_single * 1e6}
     # the same planner as 10 (main.py's numTrials) and 64 seeded trials in lock step: one launch per iteration
     from pyoptimalmotionplanning_b200.rrt import RepeatedRRTForest
-    for T, its in ((10, 4000), (64, 1500)):
+    for T, its in ((1, 20000), (10, 4000), (64, 1500)):   # T = 1: the single trial through multi-iteration launches
         rf = RepeatedRRTForest(bug, [0.1, 0.5], list(range(T)), [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01)
         rf.planMore(50)
         done0 = sum(rf.totalIters)

@@ -300,6 +300,18 @@ int pomp_forest_extend_h(pomp_forest* f, pomp_space* s, const double* xrand_h, c
                          double resolution, int64_t* parent_h, double* xnew_h, double* edge_len_h,
                          int32_t* added_h);
 
+/* n_iters (1..32) expansions per trial in ONE launch: xrand_h is [T][n_iters][dim], outputs are [T][n_iters](...).
+   Trial t executes its samples in order exactly as n_iters successive pomp_forest_extend_h calls would, except that
+   it stops after the expansion whose new node lies within goal_radius of goal_h (NULL: never) -- where
+   RepeatedRRT.planMore returns (kinodynamicplanner.py:1291-1312).  n_done_h[t] = expansions executed (0 for an
+   inactive trial); only the first n_done_h[t] output records of a trial are written.  The planner loop is bound by
+   launch + synchronisation latency; RRT's samples do not depend on the tree, so they can be drawn ahead. */
+int pomp_forest_extend_multi_h(pomp_forest* f, pomp_space* s, int32_t n_iters, const double* xrand_h,
+                               const double* root_h, const uint8_t* active_h, const uint8_t* reset_h, int check_sample,
+                               double max_step, double resolution, const double* goal_h, double goal_radius,
+                               int32_t* n_done_h, int64_t* parent_h, double* xnew_h, double* edge_len_h,
+                               int32_t* added_h);
+
 #ifdef __cplusplus
 }
 #endif

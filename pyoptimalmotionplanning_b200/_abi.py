@@ -107,6 +107,8 @@ SIGNATURES = {
     "pomp_forest_destroy": (C.c_int, [_P]),
     "pomp_forest_size": (_I64, [_P, C.c_int]),
     "pomp_forest_extend_h": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _D, _D, _P, _P, _P, _P]),
+    "pomp_forest_extend_multi_h": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.c_int, _D, _D, _P, _D, _P, _P, _P, _P,
+                                             _P]),
     "pomp_rrt_extend_h": (C.c_int, [_P, _P, _P, C.c_int, _D, _D, _P, _P, _P, _P]),
     "pomp_nn_density": (C.c_int, [_P, _P, C.c_int64, _D, _D, C.c_int, _P, _P, _P]),
     "pomp_nn_density_h": (C.c_int, [_P, _P, C.c_int64, _D, _D, C.c_int, _P, _P]),

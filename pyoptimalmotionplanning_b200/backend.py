@@ -391,6 +391,30 @@ class CudaForest(object):
                                                       self.added))
 
 
+    MAX_MULTI = 32
+
+    def extend_multi(self, space, n_iters, max_step, resolution, check_sample=True, goal=None, goal_radius=0.0):
+        """pomp_forest_extend_multi_h: n_iters expansions per trial in one launch.  Samples are read from
+        self.xrand_m ([T][n_iters][D], row-major), results land in self.n_done / parent_m / xnew_m / elen_m /
+        added_m (only the first n_done[t] records of trial t are valid)."""
+        T, D, M = self.T, self.dim, int(n_iters)
+        if getattr(self, "_m_alloc", 0) < M:
+            self.xrand_m = (C.c_double * (T * self.MAX_MULTI * D))()
+            self.n_done = (C.c_int32 * T)()
+            self.parent_m = (C.c_int64 * (T * self.MAX_MULTI))()
+            self.xnew_m = (C.c_double * (T * self.MAX_MULTI * D))()
+            self.elen_m = (C.c_double * (T * self.MAX_MULTI))()
+            self.added_m = (C.c_int32 * (T * self.MAX_MULTI))()
+            self._m_alloc = self.MAX_MULTI
+        g = None
+        if goal is not None:
+            g = (C.c_double * D)(*[float(v) for v in goal])
+        check(self.lib, self.lib.pomp_forest_extend_multi_h(self._h, space._h, M, self.xrand_m, self.root, self.active,
+                                                            self.reset, 1 if check_sample else 0, float(max_step),
+                                                            float(resolution), g, float(goal_radius), self.n_done,
+                                                            self.parent_m, self.xnew_m, self.elen_m, self.added_m))
+
+
 def launch_count():
     return _abi.load_library().pomp_launch_count()
 

@@ -272,6 +272,14 @@ struct pomp_forest {
   In* in_d = nullptr;
   Out* out_h = nullptr;
   Out* out_d = nullptr;
+  // multi-iteration launches (pomp_forest_extend_multi_h): up to MAXM expansions per trial per launch
+  static constexpr int MAXM = 32;
+  double* xr_h = nullptr;   // [T][MAXM][D] samples
+  double* xr_d = nullptr;
+  Out* outm_h = nullptr;    // [T][MAXM]
+  Out* outm_d = nullptr;
+  int32_t* ndone_h = nullptr;  // [T] expansions executed
+  int32_t* ndone_d = nullptr;
   cudaStream_t stream = nullptr;
 };
 
@@ -412,6 +420,178 @@ forest_extend_kernel(double* __restrict__ pts, int* __restrict__ count, long lon
   }
 }
 
+// M expansions per trial in ONE launch.  The planner loop is bound by launch + synchronisation latency
+// (~19 us per iteration for a 5 us kernel); RRT's samples do not depend on the tree, so the host draws the
+// samples of the next M iterations up front and the block applies them one after the other to its tree,
+// exactly as M successive forest_extend_kernel launches would.  A trial stops after the expansion whose
+// new node lies in the goal ball (RepeatedRRT.planMore returns there, kinodynamicplanner.py:1291-1312);
+// the host puts the unused random numbers back.
+__global__ void __launch_bounds__(256)
+forest_extend_multi_kernel(double* __restrict__ pts, int* __restrict__ count, long long cap, int D, SpaceDev s,
+                           const pomp_forest::In* __restrict__ in, const double* __restrict__ xr, int M,
+                           pomp_forest::Out* __restrict__ outm, int32_t* __restrict__ ndone, int check_sample,
+                           double max_step, double res, QueryArg goal, int has_goal, double goal_radius) {
+  const int t = blockIdx.x;
+  __shared__ pomp_forest::In job;
+  __shared__ int n_sh, sample_ok, stop_sh;
+  __shared__ double xrand[POMP_MAX_DIM];
+  __shared__ double sd[8];
+  __shared__ int si[8];
+  __shared__ double xn[POMP_MAX_DIM], xnew[POMP_MAX_DIM];
+  __shared__ long long ks;
+  __shared__ double elen;
+  __shared__ int parent;
+  if (threadIdx.x == 0) {
+    job = in[t];
+    int n = count[t];
+    if (job.reset) {
+      for (int j = 0; j < D; j++) pts[(long long)t * cap * D + j] = job.root[j];
+      n = 1;
+      count[t] = 1;
+    }
+    n_sh = n;
+    stop_sh = 0;
+  }
+  __syncthreads();
+  if (!job.active) {
+    if (threadIdx.x == 0) ndone[t] = 0;
+    return;
+  }
+  double* P = pts + (long long)t * cap * D;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int done = 0;
+  for (int it = 0; it < M; it++) {
+    pomp_forest::Out* o = outm + (long long)t * pomp_forest::MAXM + it;
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < D; j++) xrand[j] = xr[((long long)t * pomp_forest::MAXM + it) * D + j];
+      sample_ok = (!check_sample || feasible_pt(s, xrand)) ? 1 : 0;
+    }
+    __syncthreads();
+    const int n = n_sh;
+    done = it + 1;
+    if (!sample_ok || n >= cap) {
+      if (threadIdx.x == 0) {
+        o->parent = sample_ok ? -1 : -2;
+        o->added = 0;
+        o->overflow = (sample_ok && n >= cap) ? 1 : 0;
+        o->len = 0.0;
+      }
+      const bool full = sample_ok && n >= cap;
+      __syncthreads();
+      if (full) break;   // the host reports the capacity error
+      continue;
+    }
+    double bd = POMP_INF;
+    int bi = IDX_NONE;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      double sm = 0.0;
+      for (int j = 0; j < D; j++) {
+        double tt = P[(long long)i * D + j] - xrand[j];
+        sm = sm + tt * tt;
+      }
+      double d = sqrt(sm);
+      if (key_less(d, i, bd, bi)) {
+        bd = d;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double od = __shfl_xor_sync(FULL_MASK, bd, off);
+      int oi = __shfl_xor_sync(FULL_MASK, bi, off);
+      if (key_less(od, oi, bd, bi)) {
+        bd = od;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      sd[w] = bd;
+      si[w] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int x = 1; x < nw; x++)
+        if (key_less(sd[x], si[x], bd, bi)) {
+          bd = sd[x];
+          bi = si[x];
+        }
+      bool found = bd < POMP_INF;
+      parent = found ? bi : -1;
+      ks = -1;
+      elen = 0.0;
+      if (found) {
+        double sm = 0.0;
+        for (int j = 0; j < D; j++) {
+          xn[j] = P[(long long)bi * D + j];
+          double tt = xn[j] - xrand[j];
+          sm = sm + tt * tt;
+        }
+        double d = sqrt(sm);
+        if (d > max_step) {
+          double u = max_step / d;
+          for (int j = 0; j < D; j++) xnew[j] = xn[j] + u * (xrand[j] - xn[j]);
+        } else {
+          for (int j = 0; j < D; j++) xnew[j] = xrand[j];
+        }
+        double l = 0.0;
+        for (int j = 0; j < D; j++) {
+          double tt = xn[j] - xnew[j];
+          l = l + tt * tt;
+        }
+        elen = sqrt(l);
+        ks = edge_samples(elen, res);
+      }
+    }
+    __syncthreads();
+    int ok = 1;
+    if (parent < 0) {
+      ok = 0;
+    } else {
+      const long long total = ks + 2;
+      const double kk2 = (double)(ks + 2);
+      for (long long q = threadIdx.x; q < total && ok; q += blockDim.x) {
+        double x[POMP_MAX_DIM];
+        if (q == 0) {
+          for (int j = 0; j < D; j++) x[j] = xn[j];
+        } else if (q == 1) {
+          for (int j = 0; j < D; j++) x[j] = xnew[j];
+        } else {
+          double u = (double)(q - 1) / kk2;
+          for (int j = 0; j < D; j++) x[j] = xn[j] + u * (xnew[j] - xn[j]);
+        }
+        if (!feasible_pt(s, x)) ok = 0;
+      }
+    }
+    ok = __syncthreads_and(ok);
+    if (threadIdx.x == 0) {
+      o->parent = parent;
+      o->added = ok;
+      o->overflow = 0;
+      o->len = elen;
+      for (int j = 0; j < D; j++) o->xnew[j] = parent >= 0 ? xnew[j] : nan("");
+      if (ok) {
+        for (int j = 0; j < D; j++) P[(long long)n * D + j] = xnew[j];
+        n_sh = n + 1;
+        if (has_goal) {  // goal ball test as the host does it: sqrt(sum (x - goal)^2) <= radius
+          double sm = 0.0;
+          for (int j = 0; j < D; j++) {
+            double tt = xnew[j] - goal.v[j];
+            sm = sm + tt * tt;
+          }
+          if (sqrt(sm) <= goal_radius) stop_sh = 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (stop_sh) break;
+  }
+  if (threadIdx.x == 0) {
+    count[t] = n_sh;
+    ndone[t] = done;
+    __threadfence_system();
+  }
+}
+
 POMP_API int pomp_forest_create(int dim, int n_trials, int64_t capacity_per_trial, int device, pomp_forest** out) {
   POMP_REQUIRE(out, "out is NULL");
   *out = nullptr;
@@ -431,6 +611,13 @@ POMP_API int pomp_forest_create(int dim, int n_trials, int64_t capacity_per_tria
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->out_h, sizeof(pomp_forest::Out) * (size_t)n_trials, cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&f->in_d, f->in_h, 0);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&f->out_d, f->out_h, 0);
+  const size_t TM = (size_t)n_trials * pomp_forest::MAXM;
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->xr_h, sizeof(double) * TM * dim, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->outm_h, sizeof(pomp_forest::Out) * TM, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->ndone_h, sizeof(int32_t) * (size_t)n_trials, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&f->xr_d, f->xr_h, 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&f->outm_d, f->outm_h, 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&f->ndone_d, f->ndone_h, 0);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     set_error("pomp_forest_create: %s", cudaGetErrorString(e));
@@ -449,6 +636,9 @@ POMP_API int pomp_forest_destroy(pomp_forest* f) {
   if (f->d_count) cudaFree(f->d_count);
   if (f->in_h) cudaFreeHost(f->in_h);
   if (f->out_h) cudaFreeHost(f->out_h);
+  if (f->xr_h) cudaFreeHost(f->xr_h);
+  if (f->outm_h) cudaFreeHost(f->outm_h);
+  if (f->ndone_h) cudaFreeHost(f->ndone_h);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
   return POMP_OK;
@@ -496,6 +686,61 @@ POMP_API int pomp_forest_extend_h(pomp_forest* f, pomp_space* sp, const double* 
     for (int j = 0; j < D; j++) xnew_h[(size_t)t * D + j] = o.xnew[j];
     if (o.added) f->h_count[(size_t)t] += 1;
     overflow |= o.overflow;
+  }
+  if (overflow) {
+    set_error("a trial's tree reached the forest capacity of %lld nodes", (long long)f->cap);
+    return POMP_ERR_CAPACITY;
+  }
+  return POMP_OK;
+}
+
+POMP_API int pomp_forest_extend_multi_h(pomp_forest* f, pomp_space* sp, int32_t n_iters, const double* xrand_h,
+                                        const double* root_h, const uint8_t* active_h, const uint8_t* reset_h,
+                                        int check_sample, double max_step, double resolution, const double* goal_h,
+                                        double goal_radius, int32_t* n_done_h, int64_t* parent_h, double* xnew_h,
+                                        double* edge_len_h, int32_t* added_h) {
+  POMP_REQUIRE(f && sp && xrand_h && root_h && n_done_h && parent_h && xnew_h && added_h,
+               "NULL argument to pomp_forest_extend_multi_h");
+  POMP_REQUIRE(n_iters >= 1 && n_iters <= pomp_forest::MAXM, "n_iters=%d outside 1..%d", n_iters, pomp_forest::MAXM);
+  POMP_REQUIRE(sp->dev.dim == f->D && sp->device == f->device, "space does not match the forest");
+  POMP_REQUIRE(resolution > 0.0 && max_step >= 0.0, "bad step/resolution");
+  DeviceGuard g(f->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  const int D = f->D, T = f->T, M = n_iters, MM = pomp_forest::MAXM;
+  for (int t = 0; t < T; t++) {
+    pomp_forest::In& in = f->in_h[t];
+    for (int j = 0; j < D; j++) in.root[j] = root_h[j];
+    in.active = active_h ? (active_h[t] != 0) : 1;
+    in.reset = (reset_h ? (reset_h[t] != 0) : 0) || f->h_count[(size_t)t] == 0;
+    if (in.reset && in.active) f->h_count[(size_t)t] = 1;
+    if (!in.active) in.reset = 0;  // an inactive trial keeps its pending reset for its next active launch
+    if (in.active)
+      for (int i = 0; i < M; i++)
+        for (int j = 0; j < D; j++) f->xr_h[((size_t)t * MM + i) * D + j] = xrand_h[((size_t)t * M + i) * D + j];
+  }
+  QueryArg ga;
+  for (int j = 0; j < POMP_MAX_DIM; j++) ga.v[j] = (goal_h && j < D) ? goal_h[j] : 0.0;
+  LAUNCH(forest_extend_multi_kernel, T, 256, 0, f->stream, f->d_pts, f->d_count, (long long)f->cap, D, sp->dev, f->in_d,
+         f->xr_d, M, f->outm_d, f->ndone_d, check_sample, max_step, resolution, ga, goal_h ? 1 : 0, goal_radius);
+  CHECK_LAUNCH();
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  int overflow = 0;
+  for (int t = 0; t < T; t++) {
+    if (active_h && !active_h[t]) {
+      n_done_h[t] = 0;
+      continue;
+    }
+    const int nd = f->ndone_h[t];
+    n_done_h[t] = nd;
+    for (int i = 0; i < nd; i++) {
+      const pomp_forest::Out& o = f->outm_h[(size_t)t * MM + i];
+      parent_h[(size_t)t * M + i] = o.parent;
+      added_h[(size_t)t * M + i] = o.added;
+      if (edge_len_h) edge_len_h[(size_t)t * M + i] = o.len;
+      for (int j = 0; j < D; j++) xnew_h[((size_t)t * M + i) * D + j] = o.xnew[j];
+      if (o.added) f->h_count[(size_t)t] += 1;
+      overflow |= o.overflow;
+    }
   }
   if (overflow) {
     set_error("a trial's tree reached the forest capacity of %lld nodes", (long long)f->cap);

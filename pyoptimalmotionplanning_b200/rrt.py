@@ -16,6 +16,7 @@ configurationspace.py:38-44) or the box (BoxSet.sample: uniform(a_i,b_i), sets.p
 """
 import hashlib
 import math
+import collections
 import random
 
 from .descriptors import MetricSpec, space_from_pomp
@@ -172,6 +173,10 @@ class RRTForest(object):
         self._forest = forest_cls(self.D, self.T, capacity, device)
         self._space = space_cls(self.spec, device)
         self.rngs = [random.Random(s) for s in seeds]
+        # random numbers drawn ahead for a multi-iteration launch but not used (the trial stopped at the goal):
+        # they are the next ones the trial consumes, so every trial sees the reference's sequence
+        self._ahead = [collections.deque() for _ in seeds]
+        self.multi = hasattr(self._forest, "extend_multi")
         for j in range(self.D):
             self._forest.root[j] = self.start[j]
         self.nodes = [[self.start] for _ in range(self.T)]
@@ -201,14 +206,9 @@ class RRTForest(object):
             if not on:
                 continue
             self._pending_reset[t] = False
-            rng = self.rngs[t]
             b = t * D
-            if goal is not None and rng.uniform(0.0, 1.0) < p:
-                for j in range(D):
-                    xr[b + j] = goal[j] + rng.uniform(-r, r)
-            else:
-                for j, (lo, hi) in enumerate(self._lo_hi):
-                    xr[b + j] = rng.uniform(lo, hi)
+            for j, v in enumerate(self._draw_sample(t)[0]):
+                xr[b + j] = v
         f.extend(self._space, self.max_step, self.resolution, True)
         out = [None] * self.T
         added, parent, xnew, elen = f.added, f.parent, f.xnew, f.elen
@@ -222,6 +222,98 @@ class RRTForest(object):
                 out[t] = len(self.nodes[t]) - 1
         return out
 
+    def _u(self, t):
+        a = self._ahead[t]
+        return a.popleft() if a else self.rngs[t].random()
+
+    def _draw_sample(self, t):
+        """RRT.expand's sample for trial t (kinodynamicplanner.py:358-363): goal-biased with probability
+        pChooseGoal, else uniform in the bounds.  random.uniform(a, b) is a + (b - a) * random(); the raw random()
+        values are returned as well so that a sample drawn ahead can be handed back."""
+        goal, r = self.goal, self.goal_radius
+        raw = []
+        if goal is not None:
+            u0 = self._u(t)
+            raw.append(u0)
+            if 0.0 + (1.0 - 0.0) * u0 < self.pChooseGoal:
+                x = []
+                for j in range(self.D):
+                    u = self._u(t)
+                    raw.append(u)
+                    x.append(goal[j] + (-r + (r - (-r)) * u))
+                return x, raw
+        x = []
+        for lo, hi in self._lo_hi:
+            u = self._u(t)
+            raw.append(u)
+            x.append(lo + (hi - lo) * u)
+        return x, raw
+
+    def expand_multi(self, M, active=None, stop_at_goal=False):
+        """M expansions per active trial in ONE launch (`pomp_forest_extend_multi_h`).  Returns, per trial, the list
+        of new node indices (None where an expansion added nothing) of the expansions that were executed: all M,
+        or fewer when stop_at_goal and a new node landed in the goal ball."""
+        f, D = self._forest, self.D
+        raws = [None] * self.T
+        staged = []
+        for t in range(self.T):
+            on = active is None or active[t]
+            f.active[t] = 1 if on else 0
+            f.reset[t] = 1 if (on and self._pending_reset[t]) else 0
+            if not on:
+                continue
+            self._pending_reset[t] = False
+            rr = []
+            for it in range(M):
+                x, raw = self._draw_sample(t)
+                rr.append(raw)
+                staged.append((t, it, x))
+            raws[t] = rr
+        self._ensure_multi_buffers(M)
+        xr = f.xrand_m
+        for t, it, x in staged:
+            b = (t * M + it) * D
+            for j in range(D):
+                xr[b + j] = x[j]
+        f.extend_multi(self._space, M, self.max_step, self.resolution, True,
+                       self.goal if stop_at_goal else None, self.goal_radius if stop_at_goal else 0.0)
+        out = [None] * self.T
+        for t in range(self.T):
+            if raws[t] is None:
+                continue
+            nd = f.n_done[t]
+            left = [u for raw in raws[t][nd:] for u in raw]
+            if left:
+                self._ahead[t].extendleft(reversed(left))
+            res = []
+            for it in range(nd):
+                o = t * M + it
+                if f.added_m[o]:
+                    par = f.parent_m[o]
+                    self.nodes[t].append([f.xnew_m[o * D + j] for j in range(D)])
+                    self.parents[t].append(par)
+                    self.costs[t].append(self.costs[t][par] + f.elen_m[o])
+                    res.append(len(self.nodes[t]) - 1)
+                else:
+                    res.append(None)
+            out[t] = res
+        return out
+
+    def _ensure_multi_buffers(self, M):
+        f = self._forest
+        if hasattr(f, "_alloc_multi"):   # the CPU test double keeps plain lists
+            f._alloc_multi()
+        elif not hasattr(f, "xrand_m"):
+            import ctypes as C
+            T, D, MM = self.T, self.D, f.MAX_MULTI
+            f.xrand_m = (C.c_double * (T * MM * D))()
+            f.n_done = (C.c_int32 * T)()
+            f.parent_m = (C.c_int64 * (T * MM))()
+            f.xnew_m = (C.c_double * (T * MM * D))()
+            f.elen_m = (C.c_double * (T * MM))()
+            f.added_m = (C.c_int32 * (T * MM))()
+            f._m_alloc = MM
+
     def goal_contains(self, x):
         s = 0
         for a, b in zip(x, self.goal):
@@ -229,10 +321,17 @@ class RRTForest(object):
         return math.sqrt(s) <= self.goal_radius
 
     def planMore(self, iters):
-        for _ in range(iters):
-            for t in range(self.T):
-                self.numIters[t] += 1
-            self.expand_all()
+        left = iters
+        while left > 0:
+            M = min(left, 32) if self.multi else 1
+            if M > 1:
+                for t, res in enumerate(self.expand_multi(M)):
+                    self.numIters[t] += len(res)
+            else:
+                for t in range(self.T):
+                    self.numIters[t] += 1
+                self.expand_all()
+            left -= M
 
     def trial(self, t):
         """A read-only single-trial view (nodes / parents / getRoadmap / roadmap_hash) of trial t."""
@@ -257,17 +356,23 @@ class RepeatedRRTForest(RRTForest):
         harness's planMore(10) loop (planners/test.py:24-40) trial t reproduces the single-trial run of its seed
         iteration for iteration."""
         live = [True] * self.T
-        for _ in range(iters):
-            if not any(live):
-                break
-            new = self.expand_all(live)
-            for t, n in enumerate(new):
-                if not live[t]:
+        left = iters
+        while left > 0 and any(live):
+            M = min(left, 32) if self.multi else 1
+            if M > 1:
+                new_lists = self.expand_multi(M, live, stop_at_goal=self.goal is not None)
+            else:
+                new_lists = [None if n is None and not live[t] else [n] for t, n in enumerate(self.expand_all(live))]
+            left -= M
+            for t, res in enumerate(new_lists):
+                if not live[t] or res is None:
                     continue
-                self.numIters[t] += 1
-                self.totalIters[t] += 1
+                self.numIters[t] += len(res)
+                self.totalIters[t] += len(res)
+                n = res[-1] if res else None
                 if n is None:
                     continue
+                # only the LAST executed expansion can have reached the goal (the launch stops there)
                 if self.goal is not None and self.goal_contains(self.nodes[t][n]):
                     totalcost = self.costs[t][n] + 0
                     if self.bestPath[t] is None or totalcost < self.bestPathCost[t]:

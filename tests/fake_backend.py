@@ -171,3 +171,37 @@ class OracleForest(object):
             par, xn, el, ad = oracle_rrt_extend(self._nn[t], space, xr, max_step, resolution, check_sample)
             self.parent[t], self.elen[t], self.added[t] = par, el, 1 if ad else 0
             self.xnew[t * D:(t + 1) * D] = xn
+
+    MAX_MULTI = 32
+
+    def extend_multi(self, space, n_iters, max_step, resolution, check_sample=True, goal=None, goal_radius=0.0):
+        import math
+        T, D, M = self.T, self.dim, int(n_iters)
+        self.n_done = [0] * T
+        self.parent_m = [-1] * (T * self.MAX_MULTI)
+        self.xnew_m = [0.0] * (T * self.MAX_MULTI * D)
+        self.elen_m = [0.0] * (T * self.MAX_MULTI)
+        self.added_m = [0] * (T * self.MAX_MULTI)
+        for t in range(T):
+            if not self.active[t]:
+                continue
+            if self.reset[t] or self._nn[t] is None:
+                self._nn[t] = OracleNN(oracle.MetricSpec.euclidean(D))
+                self._nn[t].add([list(self.root)])
+            for it in range(M):
+                xr = self.xrand_m[(t * M + it) * D:(t * M + it + 1) * D]
+                par, xn, el, ad = oracle_rrt_extend(self._nn[t], space, xr, max_step, resolution, check_sample)
+                o = t * M + it
+                self.parent_m[o], self.elen_m[o], self.added_m[o] = par, el, 1 if ad else 0
+                self.xnew_m[o * D:(o + 1) * D] = xn
+                self.n_done[t] = it + 1
+                if ad and goal is not None:
+                    s = 0.0
+                    for a, b in zip(xn, goal):
+                        s = s + (a - b) * (a - b)
+                    if math.sqrt(s) <= goal_radius:
+                        break
+
+    def _alloc_multi(self):
+        if not hasattr(self, "xrand_m"):
+            self.xrand_m = [0.0] * (self.T * self.MAX_MULTI * self.dim)

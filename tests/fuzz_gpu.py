@@ -175,8 +175,18 @@ def main():
                 qs = q[sub][:60]
                 off, hits = nn.neighbors(qs, r, True)
                 ooff, ohits = oracle.nn_neighbors(m, pts, qs, r, True, mask)
-                if not ((off == ooff).all() and (hits == ohits).all()):
-                    print("MISMATCH neighbors", dict(seed=seed, round=rounds, D=D, n=n, r=r))
+                if not (len(hits) == len(ohits) and (off == ooff).all() and (hits == ohits).all()):
+                    print("MISMATCH neighbors", dict(seed=seed, round=rounds, D=D, n=n, n0=n0, r=r, masked=mask is not None,
+                                                     ppc=nn.get_stat("n_indexed") / max(nn.get_stat("n_cells"), 1)))
+                    for j in range(len(qs)):
+                        g, w = hits[off[j]:off[j + 1]], ohits[ooff[j]:ooff[j + 1]]
+                        if len(g) != len(w) or (g != w).any():
+                            print(" query", j, qs[j], "got", len(g), g[:12], "want", len(w), w[:12])
+                            extra = sorted(set(g.tolist()) ^ set(w.tolist()))[:6]
+                            for e in extra:
+                                print("   differs on", e, "dist", oracle.metric(m, pts[e], qs[j]), "r", r,
+                                      "masked" if mask is not None and mask[e] else "")
+                            break
                     return 1
         rounds += 1
         del nn
