@@ -526,3 +526,26 @@ def test_bruteforce_tiled_nearest_matches_oracle(D):
             idx, dist = nn.nearest(q)
             oi, od = oracle.nn_nearest(m, pts, q, mask)
             assert (idx == oi).all() and (dist == od).all(), (n, nq, lattice, tiled, "masked")
+
+
+def test_forest_multi_iteration_launches_equal_single_iteration_launches():
+    """pomp_forest_extend_multi_h (up to 32 expansions per launch, samples drawn ahead, early stop at the goal with
+    the unused random numbers handed back) must grow exactly the trees of the one-expansion-per-launch path."""
+    from pyoptimalmotionplanning_b200.rrt import RRTForest, RepeatedRRTForest
+    sp = SpaceSpec([0, 0], [1, 1], boxes=[[0.3, 0.3, 0.7, 0.7]])
+    seeds = [0, 1, 2, 3, 11]
+    a = RRTForest(sp, [0.1, 0.5], seeds, [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01)
+    b = RRTForest(sp, [0.1, 0.5], seeds, [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01)
+    b.multi = False
+    a.planMore(333)          # chunks of 32 + a ragged tail
+    b.planMore(333)
+    assert a.nodes == b.nodes and a.parents == b.parents and a.costs == b.costs and a.numIters == b.numIters
+    ra = RepeatedRRTForest(sp, [0.1, 0.5], seeds, [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01)
+    rb = RepeatedRRTForest(sp, [0.1, 0.5], seeds, [0.9, 0.5], 0.1, max_step=0.15, resolution=0.01)
+    rb.multi = False
+    for _ in range(120):      # the reference harness's loop: trials return at a goal hit, unused samples go back
+        ra.planMore(10)
+        rb.planMore(10)
+        assert ra.bestPathCost == rb.bestPathCost and ra.totalIters == rb.totalIters
+    assert ra.nodes == rb.nodes and ra.parents == rb.parents
+    assert any(c is not None for c in ra.bestPathCost)
