@@ -87,6 +87,9 @@ struct DevBuf {
     size_t want = n + n / 4 + 16;
     cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
     if (e == cudaSuccess) e = cudaMemset(p, 0, want * sizeof(T));  // scratch counters start from a defined state
+    // the memset runs on the legacy default stream, which the library's NON-BLOCKING streams do not wait for:
+    // without this it can land after the first kernel has already written into the new buffer
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
       return e == cudaErrorMemoryAllocation ? POMP_ERR_NOMEM : POMP_ERR_CUDA;

@@ -625,6 +625,7 @@ POMP_API int pomp_forest_create(int dim, int n_trials, int64_t capacity_per_tria
     return e == cudaErrorMemoryAllocation ? POMP_ERR_NOMEM : POMP_ERR_CUDA;
   }
   memset(f->in_h, 0, sizeof(pomp_forest::In) * (size_t)n_trials);
+  CUDA_TRY(cudaDeviceSynchronize());  // the default-stream memset above vs the non-blocking stream of the launches
   *out = f;
   return POMP_OK;
 }

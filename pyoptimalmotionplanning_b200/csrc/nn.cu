@@ -1421,6 +1421,7 @@ POMP_API int pomp_nn_create(const pomp_metric_desc* metric, int64_t capacity_hin
     delete h;
     return POMP_ERR_CUDA;
   }
+  cudaDeviceSynchronize();  // default-stream memset above vs the handle's non-blocking stream
   int rc = nn_grow(h, std::max<int64_t>(capacity_hint, 1024), h->stream);
   if (rc != POMP_OK) {
     delete h;
@@ -1919,7 +1920,7 @@ POMP_API int pomp_nn_neighbors_h(pomp_nn* h, const double* q_h, int64_t nq, doub
   }
   POMP_TRY(h->q_dev.reserve((size_t)nq * h->D));
   POMP_TRY(h->out_idx.reserve((size_t)std::max<int64_t>(idx_capacity, 1)));
-  DevBuf<int64_t> off;
+  DevBuf<int64_t>& off = h->rad_off;   // kept in the handle: no allocation per call
   POMP_TRY(off.reserve((size_t)nq + 1));
   CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, q_h, sizeof(double) * (size_t)nq * h->D, cudaMemcpyHostToDevice, st));
   int64_t needed = 0;

@@ -78,6 +78,7 @@ struct pomp_nn {
   DevBuf<double> out_dist;
   DevBuf<int32_t> out_cnt;
   DevBuf<int64_t> out_off;
+  DevBuf<int64_t> rad_off;  // CSR offsets of pomp_nn_neighbors_h
   DevBuf<int> rstage;       // radius queries: parked hit positions, RADIUS_STAGE_CAP per query
   DevBuf<double> rw_ab;     // pomp_rewire_candidates_h: the 2k edges (a then b)
   DevBuf<uint8_t> rw_ok;

@@ -488,6 +488,12 @@ POMP_API int pomp_space_create(const pomp_space_desc* d, int device, pomp_space*
   s.circles = sp->d_circles;
   int rc = build_obstacle_grid(sp, d, sp->stream);
   if (rc != POMP_OK) return fail(rc);
+  // obstacle tables were copied on the default stream; queries run on non-blocking streams
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("pomp_space_create: device synchronisation failed");
+    pomp_space_destroy(sp);
+    return POMP_ERR_CUDA;
+  }
   *out = sp;
   return POMP_OK;
 }

@@ -252,50 +252,76 @@ class RRTForest(object):
     def expand_multi(self, M, active=None, stop_at_goal=False):
         """M expansions per active trial in ONE launch (`pomp_forest_extend_multi_h`).  Returns, per trial, the list
         of new node indices (None where an expansion added nothing) of the expansions that were executed: all M,
-        or fewer when stop_at_goal and a new node landed in the goal ball."""
-        f, D = self._forest, self.D
-        raws = [None] * self.T
-        staged = []
-        for t in range(self.T):
+        or fewer when stop_at_goal and a new node landed in the goal ball.  (Hot host loop: samples are computed
+        inline from raw random() values exactly as `_draw_sample` does.)"""
+        f, D, T = self._forest, self.D, self.T
+        self._ensure_multi_buffers(M)
+        xr = f.xrand_m
+        goal, r, p, lohi = self.goal, self.goal_radius, self.pChooseGoal, self._lo_hi
+        per = D + (1 if goal is not None else 0)
+        need = M * per
+        raws = [None] * T
+        for t in range(T):
             on = active is None or active[t]
             f.active[t] = 1 if on else 0
             f.reset[t] = 1 if (on and self._pending_reset[t]) else 0
             if not on:
                 continue
             self._pending_reset[t] = False
-            rr = []
-            for it in range(M):
-                x, raw = self._draw_sample(t)
-                rr.append(raw)
-                staged.append((t, it, x))
-            raws[t] = rr
-        self._ensure_multi_buffers(M)
-        xr = f.xrand_m
-        for t, it, x in staged:
-            b = (t * M + it) * D
-            for j in range(D):
-                xr[b + j] = x[j]
+            ahead = self._ahead[t]
+            rnd = self.rngs[t].random
+            if ahead:
+                take = min(len(ahead), need)
+                raw = [ahead.popleft() for _ in range(take)]
+                if take < need:
+                    raw += [rnd() for _ in range(need - take)]
+            else:
+                raw = [rnd() for _ in range(need)]
+            raws[t] = raw
+            base = t * M * D
+            k = 0
+            for _ in range(M):
+                if goal is not None:
+                    u0 = raw[k]
+                    k += 1
+                    if u0 < p:   # random.uniform(0.0, 1.0) is 0.0 + 1.0 * random(): exactly random()
+                        for j in range(D):
+                            xr[base + j] = goal[j] + (-r + (r - (-r)) * raw[k + j])
+                    else:
+                        for j in range(D):
+                            lo, hi = lohi[j]
+                            xr[base + j] = lo + (hi - lo) * raw[k + j]
+                else:
+                    for j in range(D):
+                        lo, hi = lohi[j]
+                        xr[base + j] = lo + (hi - lo) * raw[k + j]
+                k += D
+                base += D
         f.extend_multi(self._space, M, self.max_step, self.resolution, True,
-                       self.goal if stop_at_goal else None, self.goal_radius if stop_at_goal else 0.0)
-        out = [None] * self.T
-        for t in range(self.T):
-            if raws[t] is None:
+                       goal if stop_at_goal else None, self.goal_radius if stop_at_goal else 0.0)
+        out = [None] * T
+        n_done, added_m, parent_m, xnew_m, elen_m = f.n_done, f.added_m, f.parent_m, f.xnew_m, f.elen_m
+        for t in range(T):
+            raw = raws[t]
+            if raw is None:
                 continue
-            nd = f.n_done[t]
-            left = [u for raw in raws[t][nd:] for u in raw]
-            if left:
-                self._ahead[t].extendleft(reversed(left))
+            nd = n_done[t]
+            if nd < M:
+                self._ahead[t].extendleft(reversed(raw[nd * per:]))
+            nodes, parents, costs = self.nodes[t], self.parents[t], self.costs[t]
             res = []
-            for it in range(nd):
-                o = t * M + it
-                if f.added_m[o]:
-                    par = f.parent_m[o]
-                    self.nodes[t].append([f.xnew_m[o * D + j] for j in range(D)])
-                    self.parents[t].append(par)
-                    self.costs[t].append(self.costs[t][par] + f.elen_m[o])
-                    res.append(len(self.nodes[t]) - 1)
+            o = t * M
+            for _ in range(nd):
+                if added_m[o]:
+                    par = parent_m[o]
+                    b = o * D
+                    nodes.append([xnew_m[b + j] for j in range(D)])
+                    parents.append(par)
+                    costs.append(costs[par] + elen_m[o])
+                    res.append(len(nodes) - 1)
                 else:
                     res.append(None)
+                o += 1
             out[t] = res
         return out
 

@@ -3,6 +3,7 @@
 Draws point sets (uniform, clustered, degenerate aspect ratios, duplicates), batch sizes on both sides of the
 query-sort threshold, k in 1..32, masks, tombstones and unindexed tails, and compares every answer of a random
 sample of the queries bit for bit with the brute-force oracle."""
+import os
 import sys
 import time
 import numpy as np
@@ -170,7 +171,7 @@ def main():
                     print(" query", q[sub][b], "got", idx[sub][b], dist[sub][b], "want", oi[b], od[b])
                 return 1
             checks += len(sub)
-            if rng.random() < 0.3:
+            if rng.random() < (1.0 if os.environ.get("FUZZ_RADIUS_ALWAYS") else 0.3):
                 r = float(np.median(od[:, -1][np.isfinite(od[:, -1])])) * 1.5 if np.isfinite(od[:, -1]).any() else 0.1
                 qs = q[sub][:60]
                 off, hits = nn.neighbors(qs, r, True)
