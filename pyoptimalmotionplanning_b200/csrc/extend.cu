@@ -220,27 +220,40 @@ POMP_API int pomp_rewire_candidates_h(pomp_nn* h, pomp_space* sp, const double* 
   if (!g.ok) return POMP_ERR_CUDA;
   cudaStream_t st = h->stream;
   const int D = h->D;
+  // one packed result record [idx k][dist k][count, pad][ok 2k]: a single device-to-host copy into pinned memory
+  const size_t off_dist = sizeof(int64_t) * (size_t)k, off_cnt = off_dist + sizeof(double) * (size_t)k;
+  const size_t off_ok = off_cnt + 8, pack_bytes = off_ok + 2 * (size_t)k;
   POMP_TRY(h->q_dev.reserve((size_t)D));
-  POMP_TRY(h->out_idx.reserve((size_t)k));
-  POMP_TRY(h->out_dist.reserve((size_t)k));
-  POMP_TRY(h->out_cnt.reserve(1));
   POMP_TRY(h->rw_ab.reserve((size_t)4 * k * D));
-  POMP_TRY(h->rw_ok.reserve((size_t)2 * k));
+  POMP_TRY(h->rw_ok.reserve(pack_bytes + 16));
+  if (h->rw_pin_cap < pack_bytes) {
+    if (h->rw_pin) cudaFreeHost(h->rw_pin);
+    h->rw_pin = nullptr;
+    CUDA_TRY(cudaHostAlloc(&h->rw_pin, pack_bytes + 256, cudaHostAllocDefault));
+    h->rw_pin_cap = pack_bytes + 256;
+  }
+  unsigned char* pk = h->rw_ok.p;
+  int64_t* d_idx = reinterpret_cast<int64_t*>(pk);
+  double* d_dist = reinterpret_cast<double*>(pk + off_dist);
+  int32_t* d_cnt = reinterpret_cast<int32_t*>(pk + off_cnt);
+  uint8_t* d_ok = pk + off_ok;
   CUDA_TRY(cudaMemcpyAsync(h->q_dev.p, x_h, sizeof(double) * D, cudaMemcpyHostToDevice, st));
-  POMP_TRY(pomp_nn_knearest(h, h->q_dev.p, 1, k, h->out_idx.p, h->out_dist.p, h->out_cnt.p, st));
+  POMP_TRY(pomp_nn_knearest(h, h->q_dev.p, 1, k, d_idx, d_dist, d_cnt, st));
   QueryArg qa;
   for (int j = 0; j < POMP_MAX_DIM; j++) qa.v[j] = j < D ? x_h[j] : 0.0;
   double* a = h->rw_ab.p;
   double* b = h->rw_ab.p + (size_t)2 * k * D;
-  LAUNCH(rewire_gather_kernel, (2 * k + 63) / 64, 64, 0, st, h->d_pts, D, h->out_idx.p, k, qa, a, b);
+  LAUNCH(rewire_gather_kernel, (2 * k + 63) / 64, 64, 0, st, h->d_pts, D, d_idx, k, qa, a, b);
   CHECK_LAUNCH();
-  POMP_TRY(pomp_edge_check(sp, a, b, 2 * k, resolution, h->rw_ok.p, st));
-  CUDA_TRY(cudaMemcpyAsync(idx_h, h->out_idx.p, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(dist_h, h->out_dist.p, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(count_h, h->out_cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(ok_in_h, h->rw_ok.p, (size_t)k, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(ok_out_h, h->rw_ok.p + k, (size_t)k, cudaMemcpyDeviceToHost, st));
+  POMP_TRY(pomp_edge_check(sp, a, b, 2 * k, resolution, d_ok, st));
+  CUDA_TRY(cudaMemcpyAsync(h->rw_pin, pk, pack_bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned char* hp = static_cast<const unsigned char*>(h->rw_pin);
+  memcpy(idx_h, hp, sizeof(int64_t) * (size_t)k);
+  memcpy(dist_h, hp + off_dist, sizeof(double) * (size_t)k);
+  memcpy(count_h, hp + off_cnt, sizeof(int32_t));
+  memcpy(ok_in_h, hp + off_ok, (size_t)k);
+  memcpy(ok_out_h, hp + off_ok + k, (size_t)k);
   return POMP_OK;
 }
 

@@ -1440,6 +1440,7 @@ POMP_API int pomp_nn_destroy(pomp_nn* h) {
   if (h->ticket) cudaFree(h->ticket);
   if (h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->rw_pin) cudaFreeHost(h->rw_pin);
   for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
   for (auto& cg : h->chunk_graphs)
     if (cg.exec) cudaGraphExecDestroy(cg.exec);

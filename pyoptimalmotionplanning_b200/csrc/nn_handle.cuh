@@ -81,7 +81,9 @@ struct pomp_nn {
   DevBuf<int64_t> rad_off;  // CSR offsets of pomp_nn_neighbors_h
   DevBuf<int> rstage;       // radius queries: parked hit positions, RADIUS_STAGE_CAP per query
   DevBuf<double> rw_ab;     // pomp_rewire_candidates_h: the 2k edges (a then b)
-  DevBuf<uint8_t> rw_ok;
+  DevBuf<uint8_t> rw_ok;    // packed result record of pomp_rewire_candidates_h
+  void* rw_pin = nullptr;   // its pinned host landing buffer
+  size_t rw_pin_cap = 0;
   // pinned mailbox for the single-query fast path
   void* mailbox_h = nullptr;
   void* mailbox_d = nullptr;
