@@ -534,22 +534,31 @@ __device__ __forceinline__ bool flat2d_search(const GridDev& g, const double* __
     // with several inlined copies the kernel thrashes the instruction cache.
     const double2* __restrict__ PT = reinterpret_cast<const double2*>(pts);
     const int ntail = (int)(n - g.n_indexed);
-#pragma unroll 1
-    for (int i = 0; i < total + ntail; i++) {
-      int pos;
-      double2 pv;
+    // candidate i+1 is fetched while candidate i goes through the list update (~100 cycles): with the load
+    // issued and consumed in the same iteration every candidate exposed a full load latency (28 % of the stall
+    // samples of the k = 16 kernel, profiles/r1_grid_knn_flat2d_D2_k16_details.csv)
+    auto fetch = [&](int i, int& pos, double2& pv) {
       if (i < total) {
         pos = s[0] + i;
 #pragma unroll
         for (int r = 1; r < NR; r++)
           if (i >= pre[r]) pos = s[r] + (i - pre[r]);
-        if (skip && skip[__ldg(g.sidx + pos)]) continue;
         pv = __ldg(P + pos);
       } else {
         pos = g.n_indexed + (i - total);
-        if (skip && skip[pos]) continue;
         pv = __ldg(PT + pos);
       }
+    };
+    const int nall = total + ntail;
+    int pos_n = 0;
+    double2 pv_n = make_double2(0.0, 0.0);
+    if (nall > 0) fetch(0, pos_n, pv_n);
+#pragma unroll 1
+    for (int i = 0; i < nall; i++) {
+      const int pos = pos_n;
+      const double2 pv = pv_n;
+      if (i + 1 < nall) fetch(i + 1, pos_n, pv_n);
+      if (skip && skip[i < total ? __ldg(g.sidx + pos) : pos]) continue;
       double dx = pv.x - qq[0], dy = pv.y - qq[1];
       double sq = 0.0;
       sq = sq + dx * dx;
