@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "grid.cuh"
 #include "grid_fast.cuh"
+#include "grid_se2.cuh"
 #include "nn_handle.cuh"
 #include "scan.cuh"
 #include "topk.cuh"
@@ -1117,6 +1118,33 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
       default: break;
     }
   }
+  {
+    // SE(2) product metric (R^2 x SO(2), no cost lift) on its 3-axis grid: compile-time kernel (grid_se2.cuh)
+    const pomp_metric_desc& m = h->metric;
+    const GridDev& g = h->grid;
+    const bool se2 = h->se2_fast != 0 && m.kind == POMP_METRIC_GEODESIC_PRODUCT && !m.has_cost && m.n_comp == 2 &&
+                     m.comp_kind[0] == POMP_COMP_CARTESIAN && m.comp_dim[0] == 2 && m.comp_kind[1] == POMP_COMP_SO2 &&
+                     m.comp_weight[0] > 0.0 && m.comp_weight[1] > 0.0 && h->D == 3 && g.G == 3 && g.gdim[0] == 0 &&
+                     g.gdim[1] == 1 && g.gdim[2] == 2 && g.periodic[2] == 1 && !g.periodic[0] && !g.periodic[1] &&
+                     k <= 32;
+    if (se2) {
+      const int blocks = (int)((nq + 127) / 128);
+      const uint8_t* skip = h->skip_ptr();
+#define SK(KK)                                                                                                    \
+  LAUNCH((grid_knn_se2_kernel<KK>), blocks, 128, 0, st, g, m.comp_weight[0], m.comp_weight[1], h->d_pts,            \
+         (long long)h->n_dev, skip, q, (long long)nq, qperm, k, idx, dist, cnt)
+      prof_begin(h, st);
+      if (k == 1) SK(1);
+      else if (k <= 4) SK(4);
+      else if (k <= 8) SK(8);
+      else if (k <= 16) SK(16);
+      else SK(32);
+#undef SK
+      prof_end(h, st);
+      CHECK_LAUNCH();
+      return POMP_OK;
+    }
+  }
   return launch_grid_knn_generic(h, q, nq, qperm, k, idx, dist, cnt, st);
 }
 
@@ -1594,6 +1622,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "pipe_search") h->pipe_search = value;
   else if (s == "two_stage") h->two_stage = value;
   else if (s == "block_need") h->block_need = value;
+  else if (s == "se2_fast") h->se2_fast = value;
   else if (s == "bf_tiled") h->bf_tiled = value;
   else if (s == "flat_u") h->flat_u = value;
   else if (s == "use_graphs") h->use_graphs = value;

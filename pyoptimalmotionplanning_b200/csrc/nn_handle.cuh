@@ -54,6 +54,7 @@ struct pomp_nn {
   double periodic_axes = 1;  // SO(2) components of a product metric are grid axes (wrap-around cells)
   double flat_u = 4;        // flat 2-D kernel, k = 1: candidate loads in flight per thread (4, 6 or 8)
   double bf_tiled = 1;      // brute-force regime, Euclidean k = 1 batches: shared-memory tiled kernel
+  double se2_fast = 1;      // SE(2) product metric: compile-time kernel (grid_se2.cuh) instead of the generic one
   double block_need = 0;    // k = 1: expected points in the certified ball that selects the block radius (0 = default)
   double pipe_search = 0;   // experimental: per-thread software pipeline over queries (grid_pipe.cuh); its
                             // 768 B/thread of cp.async slots leave 8 warps/SM -> 0.167 ms vs 0.117 ms (flat)

@@ -549,3 +549,37 @@ def test_forest_multi_iteration_launches_equal_single_iteration_launches():
         assert ra.bestPathCost == rb.bestPathCost and ra.totalIters == rb.totalIters
     assert ra.nodes == rb.nodes and ra.parents == rb.parents
     assert any(c is not None for c in ra.bestPathCost)
+
+
+@pytest.mark.parametrize("k", [1, 5, 16, 32])
+def test_se2_compile_time_kernel_equals_generic_kernel_and_oracle(k):
+    """grid_knn_se2_kernel performs metric_eval's operations in the same order: its answers must be IDENTICAL to
+    the generic kernel's (bit-equal distances, same indices), masks / tails / seam angles included; against the
+    oracle the usual libm-pow tolerance of the product metrics applies."""
+    m = MetricSpec.geodesic_product([("R", 2), ("SO2",)], [1.0, 0.5 / np.pi])
+    rng = np.random.default_rng(100 + k)
+    n, nq = 60000, 3000
+    pts = rng.random((n, 3)) * [1, 1, 8 * np.pi] - [0, 0, 4 * np.pi]
+    q = rng.random((nq, 3)) * [1, 1, 8 * np.pi] - [0, 0, 4 * np.pi]
+    q[:300, 2] = rng.choice([0.0, 1e-9, -1e-9, 2 * np.pi, 2 * np.pi - 1e-12, -2 * np.pi], 300)
+    q[300:600] = pts[rng.integers(0, n, 300)]
+    mask = (rng.random(n) < 0.3).astype(np.uint8)
+    res = {}
+    for fast in (1, 0):
+        nn = _nn(m, None, True)
+        nn.set_param("se2_fast", fast)
+        nn.set(pts[:n - 700])
+        nn.build_index()
+        nn.add(pts[n - 700:])          # unindexed tail
+        out = [nn.knearest(q, k)]
+        nn.set_mask(mask)
+        out.append(nn.knearest(q, k))
+        res[fast] = out
+    for a, b in zip(res[1], res[0]):
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    sub = rng.choice(nq, 400, replace=False)
+    oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
+    idx, dist, cnt = res[1][0]
+    assert (cnt[sub] == oc).all()
+    assert _near_tie_ok(m, pts, q[sub], idx[sub], oi, od)
+    np.testing.assert_allclose(dist[sub], od, rtol=1e-14)
