@@ -172,6 +172,11 @@ int pomp_space_create(const pomp_space_desc* desc, int device, pomp_space** out)
 int pomp_space_destroy(pomp_space* s);
 /* CostControlSpace.setCostMax / in-place bound updates (costspace.py:26-30) */
 int pomp_space_set_bounds(pomp_space* s, const double* lo_h, const double* hi_h);
+/* "edge_overflow" (read-and-clear): 1 if an edge check since the last read asked for more than 1e7 samples
+   (length / resolution; the reference, edgechecker.py:21-22, raises OverflowError or never returns there) --
+   such an edge is reported infeasible and the *_h entry points return POMP_ERR_INVALID; device-pointer callers
+   poll this after their stream has drained.  Also "n_boxes", "n_circles", "obstacle_grid_cells". */
+int pomp_space_get_stat(pomp_space* s, const char* name, double* out);
 
 int pomp_feasible(pomp_space* s, const double* x, int64_t n, uint8_t* ok, void* stream);
 int pomp_feasible_h(pomp_space* s, const double* x_h, int64_t n, uint8_t* ok_h);

@@ -231,6 +231,24 @@ def gen_dynamics():
     xs = [rnd_pt(rng, [0, 0, 0], [1, 1, 3]) for _ in range(60)]
     us = [rnd_pt(rng, [0, 0], [1, 1]) for _ in range(60)]
     run("adaptor_cost", {"kind": "adaptor", "x_dim": 2, "cost": "path_length"}, acost, xs, us)
+    # LTI (controlspace.py:88-112): the LQR example's double integrator (lqr.py:40-65) and a dense random system;
+    # numpy's dot goes through BLAS (FMA / blocked order), so this case carries the north-star state tolerance
+    import numpy as np
+    from pomp.spaces.controlspace import LTIControlSpace
+    from pomp.example_problems import lqr
+    lprob = lqr.lqrTest()
+    lcs = lprob.controlSpace
+    xs = [rnd_pt(rng, [-2, -2], [2, 2]) for _ in range(80)]
+    us = [[rng.uniform(-1, 1)] for _ in range(80)]
+    cases.append({"name": "lti_lqr", "spec": {"kind": "lti", "A": lcs.A.tolist(), "B": lcs.B.tolist()}, "x": xs, "u": us,
+                  "tol": 1e-12, "xnext": [lcs.nextState(x, u) for x, u in zip(xs, us)]})
+    A = np.array([[rng.uniform(-1, 1) for _ in range(4)] for _ in range(4)])
+    B = np.array([[rng.uniform(-1, 1) for _ in range(3)] for _ in range(4)])
+    dense = LTIControlSpace(None, None, A, B)
+    xs = [rnd_pt(rng, [-3] * 4, [3] * 4) for _ in range(80)]
+    us = [rnd_pt(rng, [-2] * 3, [2] * 3) for _ in range(80)]
+    cases.append({"name": "lti_dense", "spec": {"kind": "lti", "A": A.tolist(), "B": B.tolist()}, "x": xs, "u": us,
+                  "tol": 1e-12, "xnext": [dense.nextState(x, u) for x, u in zip(xs, us)]})
     dump("dynamics.json", cases)
 
 
@@ -378,6 +396,28 @@ def gen_planners():
         out["G1_rrrt_bugtrap_%s" % method] = {"seed": 0, "iters": it, "change_points": cps,
                                                "start": prob.start, "goal": prob.goal.c, "goal_radius": prob.goal.r,
                                                "space": space_spec(prob.configurationSpace)}
+    # G3: sst* on DoubleIntegrator (BASELINE config 5), G4: ao-rrt(64) on Dubins with the exact (brute-force) NN
+    # (BASELINE config 4): roadmap hash, size and best cost under a fixed seed
+    import io
+    import contextlib
+    for seed in (7, 8):
+        random.seed(seed)
+        prob = doubleintegrator.doubleIntegratorTest()
+        with contextlib.redirect_stdout(io.StringIO()):
+            planner = prob.planner("sst*", selectionRadius=0.3, witnessRadius=0.3)
+            planner.planMore(1200)
+        V, E = planner.getRoadmap()
+        key = "G3_sststar_doubleintegrator" + ("" if seed == 7 else "_seed%d" % seed)
+        out[key] = {"seed": seed, "iters": 1200, "num_nodes": len(V), "hash": roadmap_hash(V, E),
+                    "best_cost": planner.bestPathCost}
+    random.seed(7)
+    prob = dubins.dubinsCarTest()
+    with contextlib.redirect_stdout(io.StringIO()):
+        planner = prob.planner("ao-rrt", numControlSamples=64, nearestNeighborMethod="bruteforce")
+        planner.planMore(400)
+    V, E = planner.getRoadmap()
+    out["G4_aorrt64_dubins_bruteforce"] = {"seed": 7, "iters": 400, "num_nodes": len(V), "hash": roadmap_hash(V, E),
+                                           "best_cost": planner.bestPathCost}
     dump("planners.json", out)
 
 

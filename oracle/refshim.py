@@ -1,5 +1,10 @@
-"""Imports the UNMODIFIED reference (read-only checkout) for golden generation and CPU-only
-host-logic tests.  TEST INFRASTRUCTURE ONLY; the reference does not exist on the GPU box.
+"""Imports the UNMODIFIED reference for golden generation, the host-logic tests, the `-m gpu` tests that
+drive the reference's own planners through the CUDA drop-ins, and bench.py's CPU arm.
+TEST / BASELINE INFRASTRUCTURE ONLY -- the product never imports this module.
+
+Where it comes from: the read-only checkout (/root/reference) in the build container; on the GPU box, where
+that path does not exist, the verbatim copy that `make -C oracle ref` staged under oracle/_ref/ (git-ignored,
+shipped with the tree like the built libraries).
 
 pomp.example_problems does `from OpenGL.GL import *`; PyOpenGL is not installed, so no-op stub
 modules are injected (drawing code is never called).
@@ -8,7 +13,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("POMP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    env = os.environ.get("POMP_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", os.path.join(_HERE, "_ref")]:
+        if cand and os.path.isdir(os.path.join(cand, "pomp")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

@@ -90,6 +90,7 @@ SIGNATURES = {
     "pomp_space_create": (C.c_int, [_SD, C.c_int, C.POINTER(_P)]),
     "pomp_space_destroy": (C.c_int, [_P]),
     "pomp_space_set_bounds": (C.c_int, [_P, _P, _P]),
+    "pomp_space_get_stat": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
     "pomp_feasible": (C.c_int, [_P, _P, _I64, _P, _P]),
     "pomp_feasible_h": (C.c_int, [_P, _P, _I64, _P]),
     "pomp_edge_check": (C.c_int, [_P, _P, _P, _I64, _D, _P, _P]),

@@ -234,6 +234,11 @@ class CudaSpace(object):
         lo, hi = _f64(lo), _f64(hi)
         check(self.lib, self.lib.pomp_space_set_bounds(self._h, _ptr(lo), _ptr(hi)))
 
+    def get_stat(self, name):
+        out = C.c_double()
+        check(self.lib, self.lib.pomp_space_get_stat(self._h, name.encode(), C.byref(out)))
+        return out.value
+
     def feasible(self, x):
         x = _f64(x, self.dim)
         ok = np.empty(len(x), np.uint8)

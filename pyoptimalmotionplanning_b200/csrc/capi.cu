@@ -7,6 +7,7 @@ namespace pomp {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<uint64_t> g_realloc_gen{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;

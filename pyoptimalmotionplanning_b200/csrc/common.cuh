@@ -23,6 +23,7 @@ namespace pomp {
 // ---- error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<uint64_t> g_realloc_gen;  // bumped by every DevBuf reallocation (captured CUDA graphs bake scratch pointers in)
 
 #define CUDA_TRY(expr)                                                                     \
   do {                                                                                     \
@@ -81,6 +82,7 @@ struct DevBuf {
   size_t cap = 0;
   int reserve(size_t n) {  // contents NOT preserved
     if (n <= cap) return POMP_OK;
+    g_realloc_gen.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -98,6 +100,7 @@ struct DevBuf {
     return POMP_OK;
   }
   void release() {
+    if (p) g_realloc_gen.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;

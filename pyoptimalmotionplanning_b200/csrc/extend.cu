@@ -119,12 +119,12 @@ __global__ void rrt_extend_kernel(double* __restrict__ pts, long long n, int D, 
         l = l + t * t;
       }
       elen = sqrt(l);
-      ks = edge_samples(elen, res);
+      ks = edge_samples(s, elen, res);
     }
   }
   __syncthreads();
   int ok = 1;
-  if (parent < 0) {
+  if (parent < 0 || ks < 0) {  // no parent, or the edge asks for more than POMP_MAX_EDGE_SAMPLES samples
     ok = 0;
   } else {
     // endpoints + k interior samples spread over the block
@@ -179,6 +179,7 @@ POMP_API int pomp_rrt_extend_h(pomp_nn* h, pomp_space* sp, const double* xrand_h
          max_step, resolution, h->part_d.p, h->part_i.p, h->ticket, (Mailbox*)h->mailbox_d);
   CHECK_LAUNCH();
   CUDA_TRY(cudaStreamSynchronize(st));
+  POMP_TRY(space_overflow_check(sp));
   const Mailbox* mb = (const Mailbox*)h->mailbox_h;
   *parent_h = mb->idx;
   *added_h = (int32_t)mb->aux[0];
@@ -248,6 +249,7 @@ POMP_API int pomp_rewire_candidates_h(pomp_nn* h, pomp_space* sp, const double* 
   POMP_TRY(pomp_edge_check(sp, a, b, 2 * k, resolution, d_ok, st));
   CUDA_TRY(cudaMemcpyAsync(h->rw_pin, pk, pack_bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  POMP_TRY(space_overflow_check(sp));
   const unsigned char* hp = static_cast<const unsigned char*>(h->rw_pin);
   memcpy(idx_h, hp, sizeof(int64_t) * (size_t)k);
   memcpy(dist_h, hp + off_dist, sizeof(double) * (size_t)k);
@@ -395,12 +397,12 @@ forest_extend_kernel(double* __restrict__ pts, int* __restrict__ count, long lon
         l = l + tt * tt;
       }
       elen = sqrt(l);
-      ks = edge_samples(elen, res);
+      ks = edge_samples(s, elen, res);
     }
   }
   __syncthreads();
   int ok = 1;
-  if (parent < 0) {
+  if (parent < 0 || ks < 0) {  // no parent, or the edge asks for more than POMP_MAX_EDGE_SAMPLES samples
     ok = 0;
   } else {
     const long long total = ks + 2;
@@ -552,12 +554,12 @@ forest_extend_multi_kernel(double* __restrict__ pts, int* __restrict__ count, lo
           l = l + tt * tt;
         }
         elen = sqrt(l);
-        ks = edge_samples(elen, res);
+        ks = edge_samples(s, elen, res);
       }
     }
     __syncthreads();
     int ok = 1;
-    if (parent < 0) {
+    if (parent < 0 || ks < 0) {
       ok = 0;
     } else {
       const long long total = ks + 2;

@@ -1707,6 +1707,9 @@ static uint64_t launch_signature(const pomp_nn* h) {
   mix((uint64_t)(uintptr_t)h->skip_ptr());
   mix(h->grid_builds);
   mix(h->mut_count);
+  // any scratch buffer that was freed / regrown since the capture (a batch of another size, a radius or density
+  // call, another handle): the graph's baked-in pointers may dangle -- recapture
+  mix(pomp::g_realloc_gen.load(std::memory_order_relaxed));
   return x | 1ull;
 }
 

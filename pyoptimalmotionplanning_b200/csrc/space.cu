@@ -36,7 +36,8 @@ __device__ __forceinline__ bool edge_linear(const SpaceDev& s, const double* a, 
       l = l + t * t;
     }
   l = sqrt(l);
-  long long k = edge_samples(l, res);
+  long long k = edge_samples(s, l, res);
+  if (k < 0) return false;
   if (!feasible_pt(s, a) || !feasible_pt(s, b)) return false;
   double dlt[DA];
 #pragma unroll
@@ -78,8 +79,8 @@ __device__ __forceinline__ bool edge_batch_warp2d(const SpaceDev& s, double2 a, 
   l = l + t0 * t0;
   l = l + t1 * t1;
   l = sqrt(l);
-  long long k = edge_samples(l, res);
-  bool alive = valid && feasible_pt(s, pa) && feasible_pt(s, pb);
+  long long k = valid ? edge_samples(s, l, res) : 0;
+  bool alive = valid && k >= 0 && feasible_pt(s, pa) && feasible_pt(s, pb);
   const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
   bool big = k > 4096;  // pathological resolution: this lane walks its own edge afterwards
   int cnt = (alive && !big) ? (int)k : 0;
@@ -220,12 +221,12 @@ __global__ void edge_check_path_kernel(SpaceDev s, pomp_metric_desc g, const dou
     l += metric_eval(g, a, b);
     for (int j = 0; j < D; j++) a[j] = b[j];
   }
-  long long k = edge_samples(l, res);
+  long long k = edge_samples(s, l, res);
   for (int j = 0; j < D; j++) {
     a[j] = P[j];
     b[j] = P[(long long)(np - 1) * D + j];
   }
-  if (!feasible_pt(s, a) || !feasible_pt(s, b)) {
+  if (k < 0 || !feasible_pt(s, a) || !feasible_pt(s, b)) {
     ok[pi] = 0;
     return;
   }
@@ -266,8 +267,8 @@ __global__ void edge_check_control_kernel(SpaceDev s, pomp_dyn_desc dy, pomp_met
   }
   if (dy.kind == POMP_DYN_DUBINS) {  // DubinsCarInterpolator (dubins.py:62-73)
     dubins_next(x, u[0], u[1], nxt);
-    long long k = edge_samples(fabs(u[0]), res);
-    bool good = feasible_pt(s, x) && feasible_pt(s, nxt);
+    long long k = edge_samples(s, fabs(u[0]), res);
+    bool good = k >= 0 && feasible_pt(s, x) && feasible_pt(s, nxt);
     const double kk2 = (double)(k + 2);
     for (long long i = 0; good && i < k; i++) {
       double uu = (double)(i + 1) / kk2;
@@ -291,8 +292,8 @@ __global__ void edge_check_control_kernel(SpaceDev s, pomp_dyn_desc dy, pomp_met
     np++;
     t = fmin(t + dt0, duration);
   }
-  long long k = edge_samples(l, res);
-  if (!feasible_pt(s, x) || !feasible_pt(s, cur)) {
+  long long k = edge_samples(s, l, res);
+  if (k < 0 || !feasible_pt(s, x) || !feasible_pt(s, cur)) {
     ok[ei] = 0;
     return;
   }
@@ -486,6 +487,12 @@ POMP_API int pomp_space_create(const pomp_space_desc* d, int device, pomp_space*
   }
   s.boxes = sp->d_boxes;
   s.circles = sp->d_circles;
+  if (cudaHostAlloc((void**)&sp->overflow_h, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&s.overflow, sp->overflow_h, 0) != cudaSuccess) {
+    set_error("mapped flag allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(POMP_ERR_CUDA);
+  }
+  *sp->overflow_h = 0;
   int rc = build_obstacle_grid(sp, d, sp->stream);
   if (rc != POMP_OK) return fail(rc);
   // obstacle tables were copied on the default stream; queries run on non-blocking streams
@@ -507,8 +514,23 @@ POMP_API int pomp_space_destroy(pomp_space* sp) {
   if (sp->d_cell_items) cudaFree(sp->d_cell_items);
   if (sp->d_cell_geom) cudaFree(sp->d_cell_geom);
   if (sp->stream) cudaStreamDestroy(sp->stream);
+  if (sp->overflow_h) cudaFreeHost(sp->overflow_h);
   delete sp;
   return POMP_OK;
+}
+
+POMP_API int pomp_space_get_stat(pomp_space* sp, const char* name, double* out) {
+  POMP_REQUIRE(sp && name && out, "NULL argument to pomp_space_get_stat");
+  if (!strcmp(name, "edge_overflow")) {  // read-and-clear; valid once the stream of the checked call has drained
+    *out = sp->overflow_h ? (double)*sp->overflow_h : 0.0;
+    if (sp->overflow_h) *sp->overflow_h = 0;
+    return POMP_OK;
+  }
+  if (!strcmp(name, "n_boxes")) { *out = sp->dev.n_boxes; return POMP_OK; }
+  if (!strcmp(name, "n_circles")) { *out = sp->dev.n_circles; return POMP_OK; }
+  if (!strcmp(name, "obstacle_grid_cells")) { *out = sp->dev.use_grid ? (double)sp->dev.gnx * sp->dev.gny : 0.0; return POMP_OK; }
+  set_error("unknown stat '%s'", name);
+  return POMP_ERR_INVALID;
 }
 
 POMP_API int pomp_space_set_bounds(pomp_space* sp, const double* lo_h, const double* hi_h) {
@@ -643,7 +665,7 @@ POMP_API int pomp_edge_check_control(pomp_space* sp, const pomp_dyn_desc* dyn, c
 static int finish_ok(pomp_space* sp, uint8_t* ok_h, int64_t n, cudaStream_t st) {
   CUDA_TRY(cudaMemcpyAsync(ok_h, sp->out_ok.p, (size_t)n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  return POMP_OK;
+  return space_overflow_check(sp);
 }
 
 POMP_API int pomp_feasible_h(pomp_space* sp, const double* x_h, int64_t n, uint8_t* ok_h) {

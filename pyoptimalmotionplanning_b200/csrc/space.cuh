@@ -24,6 +24,7 @@ struct SpaceDev {
   const int* cell_items;  // obstacle ids: boxes first, then n_boxes + circle id
   const double* cell_geom;  // the same items with their geometry inline, 4 doubles each: box (x0,y0,x1,y1) or
                             // circle (cx,cy,r,NaN) -- one dependent load less per candidate than id -> table
+  int* overflow;            // mapped pinned flag: an edge asked for more than POMP_MAX_EDGE_SAMPLES samples
 };
 
 __host__ __device__ __forceinline__ int obs_cell(double x, double lo, double inv, int n) {
@@ -81,11 +82,20 @@ __device__ __forceinline__ bool feasible_pt(const SpaceDev& s, const double* x) 
   return !hits_obstacle(s, x[s.od0], x[s.od1]);
 }
 
-// EpsilonEdgeChecker sample count (edgechecker.py:21-22): k = int(ceil(l / resolution))
-__device__ __forceinline__ long long edge_samples(double l, double res) {
+// EpsilonEdgeChecker sample count (edgechecker.py:21-22): k = int(ceil(l / resolution)).
+// More than POMP_MAX_EDGE_SAMPLES samples (a tiny resolution, or an infinite / huge edge in a space
+// with unbounded bounds) would keep one thread busy until the watchdog fires; the reference raises
+// OverflowError or never returns there.  Such an edge is reported infeasible, returns -1 here and
+// raises the space's overflow flag (mapped pinned memory: the *_h entry points turn it into
+// POMP_ERR_INVALID, device-pointer callers read it with pomp_space_get_stat("edge_overflow")).
+constexpr double POMP_MAX_EDGE_SAMPLES = 1e7;
+__device__ __forceinline__ long long edge_samples(const SpaceDev& s, double l, double res) {
   double c = ceil(l / res);
-  if (!(c > 0.0)) return 0;
-  if (c > 1e15) return 1000000000000000LL;
+  if (!(c > 0.0)) return 0;  // also NaN
+  if (c > POMP_MAX_EDGE_SAMPLES) {
+    if (s.overflow) *s.overflow = 1;
+    return -1;
+  }
   return (long long)c;
 }
 
@@ -103,4 +113,15 @@ struct pomp_space {
   pomp::DevBuf<double> in_a, in_b;
   pomp::DevBuf<int32_t> in_i;
   pomp::DevBuf<uint8_t> out_ok;
+  int* overflow_h = nullptr;  // host alias of dev.overflow
 };
+
+// after a stream synchronisation: turns a raised overflow flag into POMP_ERR_INVALID (and clears it)
+inline int space_overflow_check(pomp_space* sp) {
+  if (sp && sp->overflow_h && *sp->overflow_h) {
+    *sp->overflow_h = 0;
+    pomp::set_error("an edge asks for more than %.0f samples (length / resolution)", pomp::POMP_MAX_EDGE_SAMPLES);
+    return POMP_ERR_INVALID;
+  }
+  return POMP_OK;
+}

@@ -34,20 +34,52 @@ class DeviceSpace(object):
     def __init__(self, space, device=0, _backend_factory=None):
         self.space = space
         self.spec = space_from_pomp(space)
-        self._be = (_backend_factory or _space_backend)(self.spec, device)
+        self._factory = _backend_factory or _space_backend
+        self._device = device
+        self._be = self._factory(self.spec, device)
         self._tracks_pomp = not isinstance(space, SpaceSpec)
+        self._obstacle_fp = self._bounds_and_fingerprint(space)[2] if self._tracks_pomp else None
 
     def dimension(self):
         return self.spec.dim
 
+    @staticmethod
+    def _bounds_and_fingerprint(space):
+        """(lo, hi, fingerprint of the obstacle lists) read WITHOUT re-translating the obstacles: O(components),
+        not O(obstacles), per call."""
+        comps = getattr(space, "components", None)
+        lo, hi, fp = [], [], []
+        for c in (comps if comps is not None else [space]):
+            box = getattr(c, "box", None)
+            if box is not None and hasattr(box, "bmin"):
+                lo += list(box.bmin)
+                hi += list(box.bmax)
+            else:
+                d = c.dimension()
+                lo += [-math.inf] * d
+                hi += [math.inf] * d
+            obs = getattr(c, "obstacles", None)
+            if obs is not None:
+                fp.append((id(obs), len(obs)))
+        return lo, hi, tuple(fp)
+
     def _refresh_bounds(self):
-        # CostControlSpace.setCostMax mutates bounds in place (costspace.py:26-30)
+        # CostControlSpace.setCostMax mutates bounds in place (costspace.py:26-30); an addObstacle() after
+        # construction (geometric.py:62-63) changes the obstacle list: the device tables are rebuilt then
         if not self._tracks_pomp:
             return
-        cur = space_from_pomp(self.space)
-        if cur.lo != self.spec.lo or cur.hi != self.spec.hi:
-            self.spec.lo, self.spec.hi = cur.lo, cur.hi
-            self._be.set_bounds(cur.lo, cur.hi)
+        lo, hi, fp = self._bounds_and_fingerprint(self.space)
+        if fp != self._obstacle_fp:
+            self.spec = space_from_pomp(self.space)
+            self._be = self._factory(self.spec, self._device)
+            self._obstacle_fp = fp
+            self.bounds_version = getattr(self, "bounds_version", 0) + 1
+            return
+        lo = [float(v) for v in lo]
+        hi = [float(v) for v in hi]
+        if lo != self.spec.lo or hi != self.spec.hi:
+            self.spec.lo, self.spec.hi = lo, hi
+            self._be.set_bounds(lo, hi)
             self.bounds_version = getattr(self, "bounds_version", 0) + 1
 
     def feasible(self, x):
@@ -78,7 +110,14 @@ class EpsilonEdgeChecker(object):
     def prefetch_ready(self, nn_backend):
         """The batch call needs both back ends on the device library (or both test fakes)."""
         self._dev._refresh_bounds()
-        return hasattr(nn_backend, "rewire_candidates") and self._dev._be is not None
+        be = self._dev._be
+        if not hasattr(nn_backend, "rewire_candidates") or be is None:
+            return False
+        # pomp_rewire_candidates_h needs the space and the node set in the same coordinates on the same device
+        # (a CostMetric / state-lifted NearestNeighbors has dim + 1): otherwise the plain k-NN path answers
+        if getattr(nn_backend, "dim", None) != self._dev.spec.dim:
+            return False
+        return getattr(nn_backend, "device", 0) == getattr(be, "device", 0)
 
     def prime(self, x, neighbours, ok_in, ok_out):
         tx = tuple(x)
@@ -91,8 +130,8 @@ class EpsilonEdgeChecker(object):
 
     # ---- reference API
     def feasible(self, interpolator):
-        be = self._dev._be
         self._dev._refresh_bounds()
+        be = self._dev._be
         name = type(interpolator).__name__
         if name == "LinearInterpolator":  # interpolators.py:28-35
             if (self._rewire is not None and self._rewire[0] == self.resolution
@@ -121,6 +160,7 @@ class EpsilonEdgeChecker(object):
 
     def visible(self, a, b):
         """Klamp't-style visibility: the straight edge a->b (space.interpolator(a,b)) is feasible."""
+        self._dev._refresh_bounds()
         return self._dev._be.edge_check_one(a, b, self.resolution)
 
     # ---- batched extras

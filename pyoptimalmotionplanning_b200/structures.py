@@ -38,6 +38,7 @@ class NearestNeighbors(object):
         self._sig = None
         self._dim = metric.dim if isinstance(metric, MetricSpec) else None
         self._rewire_checker = None
+        self.generation = 0   # bumped whenever insertion indices are renumbered (set(), reset(), compaction)
         self._clear_host()
 
     def enable_rewire_prefetch(self, checker):
@@ -95,6 +96,7 @@ class NearestNeighbors(object):
 
     # ------------------------------------------------------------------ reference API
     def reset(self):
+        self.generation += 1
         self._clear_host()
         if self._be is not None:
             self._be.reset()
@@ -134,6 +136,7 @@ class NearestNeighbors(object):
         if datas is None:
             datas = [None] * len(points)
         datas = list(datas)
+        self.generation += 1
         self._clear_host()
         if self._be is not None:
             self._be.reset()
@@ -273,6 +276,11 @@ class NearestNeighbors(object):
             self._be.set_mask(None)
 
     def _maybe_compact(self):
+        """Once half of the entries are dead the set is rebuilt from the live ones.  Insertion indices handed out
+        by the *_batch methods / item() are renumbered by that: they are valid only while `generation` is
+        unchanged (compare it before and after a remove()); set `auto_compact = False` to keep indices stable."""
+        if not getattr(self, "auto_compact", True):
+            return
         n = len(self._points)
         if n < _COMPACT_MIN or self._ndead * 2 < n:
             return

@@ -60,4 +60,8 @@ def dyn_spec(s):
         return DynamicsSpec(_abi.DYN_FLAPPY, 3, 2, cost, p=s["p"])
     if k == "adaptor":
         return DynamicsSpec(_abi.DYN_ADAPTOR, s["x_dim"], s["x_dim"], cost)
+    if k == "lti":
+        import numpy as np
+        A, B = np.asarray(s["A"], dtype=np.float64), np.asarray(s["B"], dtype=np.float64)
+        return DynamicsSpec(_abi.DYN_LTI, A.shape[0], B.shape[1], cost, A=A, B=B)
     raise ValueError(k)

@@ -69,6 +69,22 @@ def _metrics():
     }
 
 
+def _hits_equal_mod_boundary(m, pts, q, r, off, hits, ooff, ohits):
+    """Radius hits as SETS per query; a point may be missing / extra only if its distance is within 2 ulp of the
+    radius (x*x on the device vs libm pow(x, 2) in the reference)."""
+    assert len(off) == len(ooff)
+    for j in range(len(off) - 1):
+        a, b = set(hits[off[j]:off[j + 1]].tolist()), set(ohits[ooff[j]:ooff[j + 1]].tolist())
+        for i in a ^ b:
+            d = oracle.metric(m, pts[i], q[j])
+            if abs(d - r) > 2 * np.spacing(r):
+                return False
+        got = hits[off[j]:off[j + 1]]
+        if (np.diff(got) <= 0).any():     # insertion order, no duplicates
+            return False
+    return True
+
+
 def _near_tie_ok(m, pts, q, got_idx, want_idx, want_dist):
     """Metrics that square through libm pow in the reference can flip candidates that are within
     a couple of ulps of each other; accept those and nothing else."""
@@ -112,7 +128,7 @@ def test_general_metrics_match_oracle(name, grid):
     if exact:
         assert (off == ooff).all() and (hits == ohits).all()
     else:
-        assert abs(int(off[-1]) - int(ooff[-1])) <= 2
+        assert _hits_equal_mod_boundary(m, pts, q[:100], 0.05 * float(np.max(hi - lo)), off, hits, ooff, ohits)
 
 
 def test_masks_tombstones_and_tail():
@@ -422,7 +438,7 @@ def test_so2_periodic_axis_wraps_and_normalises():
         np.testing.assert_allclose(dist, od, rtol=1e-14)
         off, hits = nn.neighbors(q[:150], 0.05)
         ooff, ohits = oracle.nn_neighbors(m, pts, q[:150], 0.05, True)
-        assert abs(int(off[-1]) - int(ooff[-1])) <= 2
+        assert _hits_equal_mod_boundary(m, pts, q[:150], 0.05, off, hits, ooff, ohits)
 
 
 def test_rewire_candidates_match_oracle():
@@ -583,3 +599,116 @@ def test_se2_compile_time_kernel_equals_generic_kernel_and_oracle(k):
     assert (cnt[sub] == oc).all()
     assert _near_tie_ok(m, pts, q[sub], idx[sub], oi, od)
     np.testing.assert_allclose(dist[sub], od, rtol=1e-14)
+
+
+def _numpy_merge(idx_in, dist_in, k):
+    """(distance, global index) merge of G candidate lists per query -- the rule of SURVEY 8e."""
+    G, nq, _ = idx_in.shape
+    ii = np.transpose(idx_in, (1, 0, 2)).reshape(nq, -1)
+    dd = np.transpose(dist_in, (1, 0, 2)).reshape(nq, -1).copy()
+    dd[ii < 0] = np.inf
+    key_i = np.where(ii < 0, np.iinfo(np.int64).max, ii)
+    order = np.lexsort((key_i, dd), axis=1)[:, :k]
+    oi = np.take_along_axis(ii, order, 1)
+    od = np.take_along_axis(dd, order, 1)
+    oi[np.isinf(od)] = -1
+    return oi, od
+
+
+@pytest.mark.parametrize("k", [1, 16, 40, 100])
+@pytest.mark.parametrize("G", [2, 3, 8])
+def test_merge_candidates_kernel_matches_lexsort_merge(G, k):
+    """pomp_nn_merge_candidates (the kernel behind the NCCL node-sharded path) against the NumPy merge the gloo
+    test uses, including short lists (-1 / +inf padding) and exact cross-shard distance ties."""
+    import torch
+    from pyoptimalmotionplanning_b200.backend import merge_candidates_device
+    rng = np.random.default_rng(1000 * G + k)
+    nq = 3000
+    dist_in = np.sort(rng.random((G, nq, k)), axis=2)
+    dist_in[:, :500] = np.round(dist_in[:, :500] * 8) / 8          # many exact ties across shards
+    dist_in = np.sort(dist_in, axis=2)
+    idx_in = rng.permutation(G * nq * k).reshape(G, nq, k).astype(np.int64)
+    # within a shard, equal distances must come in index order (that is what a shard's k-NN returns)
+    for g in range(G):
+        order = np.lexsort((idx_in[g], dist_in[g]), axis=1)
+        idx_in[g] = np.take_along_axis(idx_in[g], order, 1)
+        dist_in[g] = np.take_along_axis(dist_in[g], order, 1)
+    short = rng.integers(0, k + 1, (G, nq))
+    short[:, 1000:] = k
+    for g in range(G):
+        pad = np.arange(k)[None, :] >= short[g][:, None]
+        idx_in[g][pad] = -1
+        dist_in[g][pad] = np.inf
+    ti, td = torch.from_numpy(idx_in).cuda(), torch.from_numpy(dist_in).cuda()
+    oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+    oc = torch.empty(nq, dtype=torch.int32, device="cuda")
+    merge_candidates_device(ti.data_ptr(), td.data_ptr(), G, nq, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    wi, wd = _numpy_merge(idx_in, dist_in, k)
+    assert (oi.cpu().numpy() == wi).all()
+    assert (od.cpu().numpy() == wd).all()
+    assert (oc.cpu().numpy() == (wi >= 0).sum(1)).all()
+
+
+def test_node_sharded_answer_equals_single_index_on_one_gpu():
+    """The node-sharded k-NN pipeline of sharded.py with its collectives replaced by slicing (one process, G
+    shards on one GPU): local top-k per shard + pomp_nn_merge_candidates == one index over all the points."""
+    import torch
+    from pyoptimalmotionplanning_b200.backend import CudaNN, merge_candidates_device
+    rng = np.random.default_rng(5)
+    G, n, nq, k = 4, 120000, 40000, 8
+    pts = rng.random((G * n, 2))
+    pts[n + 5] = pts[7]                                   # cross-shard duplicate: tie broken by global index
+    q = rng.random((nq, 2))
+    m = MetricSpec.euclidean(2)
+    whole = _nn(m, pts, grid=True)
+    wi, wd, _ = whole.knearest(q, k)
+    st = torch.cuda.current_stream().cuda_stream
+    qd = torch.from_numpy(q).cuda()
+    ci = torch.empty((G, nq, k), dtype=torch.int64, device="cuda")
+    cd = torch.empty((G, nq, k), dtype=torch.float64, device="cuda")
+    shards = []
+    for g in range(G):
+        nn = CudaNN(m, 0)
+        nn.set(pts[g * n:(g + 1) * n])
+        nn.knearest_device(qd.data_ptr(), nq, k, ci[g].data_ptr(), cd[g].data_ptr(), None, st)
+        shards.append(nn)
+        ci[g] = torch.where(ci[g] >= 0, ci[g] + g * n, ci[g])
+    oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+    merge_candidates_device(ci.data_ptr(), cd.data_ptr(), G, nq, k, oi.data_ptr(), od.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    assert (oi.cpu().numpy() == wi).all() and (od.cpu().numpy() == wd).all()
+
+
+def test_graph_replay_survives_interleaved_batch_sizes():
+    """the pipelined host call replays captured CUDA graphs that bake scratch pointers in.  A batch of
+    another size (or a radius call) in between may regrow that scratch: the graphs must be recaptured, not
+    replayed on freed memory."""
+    rng = np.random.default_rng(41)
+    m = MetricSpec.euclidean(2)
+    pts = rng.random((400000, 2))
+    nn = _nn(m, pts, grid=True)
+    big = rng.random((200000, 2))
+    mid = rng.random((120000, 2))
+    kd = oracle.KDTree(m, pts)
+    sub = rng.choice(200000, 2000, replace=False)
+    want_i, want_d = kd.nearest(big[sub])
+    for _ in range(3):                       # direct run, capture, replay
+        i, d = nn.nearest(big)
+        assert (i[sub] == want_i).all() and (d[sub] == want_d).all()
+    mi, md = nn.nearest(mid)                 # single-pass size between the chunk sizes: regrows scratch
+    oi, od = kd.nearest(mid[:2000])
+    assert (mi[:2000] == oi).all() and (md[:2000] == od).all()
+    nn.neighbors(mid[:50000], 0.002)
+    nn.knearest(rng.random((300000, 2)), 4)
+    for _ in range(3):
+        i, d = nn.nearest(big)
+        assert (i[sub] == want_i).all() and (d[sub] == want_d).all()
+        full_i, full_d = i, d
+    ref = _nn(m, pts, grid=True)
+    ref.set_param("use_graphs", 0)
+    ri, rd = ref.nearest(big)
+    assert (full_i == ri).all() and (full_d == rd).all()

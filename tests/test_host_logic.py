@@ -279,6 +279,8 @@ def test_unmodified_sst_star_with_dropins_matches_reference():
     h_new, n_new, p_new = _run_ref_planner(lambda: make(True), 1200, True)
     assert (h_new, n_new) == (h_ref, n_ref)
     assert p_new.bestPathCost == p_ref.bestPathCost
+    g = G.load("planners.json")["G3_sststar_doubleintegrator"]      # frozen output of the unmodified reference
+    assert g["hash"] == h_new and g["num_nodes"] == n_new and g["best_cost"] == p_new.bestPathCost
 
 
 @needs_ref
@@ -304,6 +306,8 @@ def test_unmodified_ao_rrt_dubins_with_dropins_matches_bruteforce_reference():
     h_ref, n_ref, p_ref = _run_ref_planner(lambda: make(False), 400, False)
     h_new, n_new, p_new = _run_ref_planner(lambda: make(True), 400, True)
     assert (h_new, n_new) == (h_ref, n_ref)
+    g = G.load("planners.json")["G4_aorrt64_dubins_bruteforce"]
+    assert g["hash"] == h_new and g["num_nodes"] == n_new
 
 
 @needs_ref
