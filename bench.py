@@ -285,7 +285,7 @@ def run_extras(peak):
         pts = torch.from_numpy(gen_points(n, d)).cuda()
         q = torch.from_numpy(gen_queries(nq, d)).cuda()
         nn = CudaNN(MetricSpec.euclidean(d), 0)
-        for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift"):
+        for name in ("points_per_cell", "block_search", "block_need", "sort_queries", "sort_shift", "strip_search", "strip_min_per_tile", "strip_spin_ns", "strip_probe"):
             if "POMP_" + name.upper() in os.environ:
                 nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
         nn.set_device(pts.data_ptr(), n, st)
@@ -651,7 +651,7 @@ def run_gpu(args):
     q_slice_h = torch.from_numpy(q_all_h).pin_memory()
     pts = torch.from_numpy(pts_h).cuda(local)
     nn = CudaNN(MetricSpec.euclidean(DIM), local)
-    for name in ("points_per_cell", "block_search", "tile_search", "stream_search", "pipe_search", "two_stage", "block_need", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks", "use_graphs", "pipeline_shape", "flat_u"):
+    for name in ("points_per_cell", "block_search", "block_need", "sort_queries", "sort_shift", "pipeline_chunks", "overlap_chunks", "use_graphs", "pipeline_shape", "strip_search", "strip_min_per_tile", "strip_spin_ns", "strip_probe"):
         if "POMP_" + name.upper() in os.environ:   # tuning experiments
             nn.set_param(name, float(os.environ["POMP_" + name.upper()]))
     nn.set_device(pts.data_ptr(), n, st)
@@ -777,7 +777,7 @@ def run_gpu(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(world),
-                "roofline": {"bound": "hbm", "kernel": "grid_knn_flat2d_kernel<1,1>", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "strip_nn_kernel<1>" if nn.get_stat("strip_launches") > 0 else "grid_knn_flat2d_kernel<1,1>", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kms,
                              "kernel_share_of_step": kms / ms_step if ms_step > 0 else None,

@@ -31,6 +31,18 @@ struct GridDev {
   int periodic[POMP_MAX_DIM];   // axis is an SO(2) angle: bucketed by so2_normalize(x) over [0, 2 pi), wraps around
 };
 
+// blocked ("strip") copy of a 2-D grid index for the streaming nearest-neighbour kernel, see strip2d.cuh
+struct StripDev {
+  int W, H;            // cells of the underlying grid
+  int nstrips, nty;    // strips along x, tiles per strip
+  int ntiles;
+  const double2* spts2;      // replicated, strip-major points
+  const int* sidx2;          // insertion index per slot
+  const int2* tile_info;     // (first slot, slots) of tile + halo
+  const uint16_t* tile_cs;   // ST_CS_STRIDE offsets per tile
+  long long nslots;
+};
+
 // monotone in x by construction (fl subtraction, fl multiply, truncation, clamping)
 __device__ __forceinline__ int grid_cell(const GridDev& g, int a, double x) {
   double t = (x - g.lo[a]) * g.inv_h[a];

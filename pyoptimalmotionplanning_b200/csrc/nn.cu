@@ -1019,7 +1019,6 @@ struct SortInfo {
   const double* qsorted = nullptr;
   const int* qstart = nullptr;
   int shift = 0, nbx = 0;
-  bool tile_major = false;
 };
 
 static bool knn_is_fast(const pomp_nn* h, int k) { return is_plain_euclid(h->metric) && h->grid.G == h->D && k <= 32; }
@@ -1033,11 +1032,10 @@ static int grid_knn_sort(pomp_nn* h, SortScratch& S, const double* q, int64_t nq
   S.ovf_zeroed = false;
   if (!(h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff)) return POMP_OK;
   int shift = 0;
-  // 2^shift-cell bins along axis 0 (6 = the experimental tile kernels' TW)
-  if (h->grid.ncell[0] >= 256) shift = (fast && h->D == 2 && h->stream_search != 0) ? 6 : (int)h->sort_shift;
+  // 2^shift-cell bins along axis 0
+  if (h->grid.ncell[0] >= 256) shift = (int)h->sort_shift;
   int nbx = (h->grid.ncell[0] + (1 << shift) - 1) >> shift;
-  const bool tile_major = fast && h->D == 2 && h->stream_search != 0 && shift == 6;  // bins = 64 x 8-cell tiles
-  const int row_div = tile_major ? 8 : 1;
+  const int row_div = 1;
   long long nrow = h->grid.n_cells / h->grid.ncell[0];
   long long nb = ((nrow + row_div - 1) / row_div) * nbx;
   POMP_TRY(S.counts.reserve((size_t)nb + 1 + (size_t)nb + 1));
@@ -1064,7 +1062,6 @@ static int grid_knn_sort(pomp_nn* h, SortScratch& S, const double* q, int64_t nq
   if (fast && h->D == 2) info->qsorted = S.qsorted.p;
   info->shift = shift;
   info->nbx = nbx;
-  info->tile_major = tile_major;
   return POMP_OK;
 }
 
@@ -1076,22 +1073,10 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
   const int* qstart = si.qstart;
   const int shift = si.shift, nbx = si.nbx;
   const bool fast = knn_is_fast(h, k);
-  const bool tile = fast && h->D == 2 && (h->tile_search != 0 || h->stream_search != 0);
+  (void)qstart;
+  (void)shift;
+  (void)nbx;
   if (fast) {
-    if (tile && qsorted) {
-      const int KK = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32)));
-      double ppc = (double)h->grid.n_indexed / (double)h->grid.n_cells;
-      int R = 1;
-      while (R < 6 && ppc * 3.141592653589793 * R * R < 2.5 * KK + 3.0) R++;
-      if (R <= 3 && shift == 6 && h->stream_search != 0 && si.tile_major) {  // 3 = TILE_RMAX (grid_tile.cuh)
-        int rc = launch_grid_knn_stream2d(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
-        if (rc <= 0) return rc;
-      }
-      if (R <= 3 && shift == 6 && h->tile_search != 0 && !si.tile_major) {
-        int rc = launch_grid_knn_tile2d_64(h, q, nq, qperm, qsorted, qstart, nbx, k, R, idx, dist, cnt, st);
-        if (rc <= 0) return rc;
-      }
-    }
     switch (h->D) {
       case 2: {
         if (h->block_search != 0) {
@@ -1155,6 +1140,8 @@ static int grid_knn(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx
                     cudaStream_t st) {
   const bool sorting = h->sort_queries != 0 && nq >= (int64_t)h->sort_min_queries && h->grid.n_cells <= 0x7fffffff;
   const int C = (int)h->overlap_chunks;
+  // dense 2-D nearest() batches: streaming kernel over the strip index (strip2d.cu), tile-major query sort
+  if (strip_eligible(h, nq, k)) return strip_nearest(h, q, nq, k, idx, dist, cnt, st);
   if (!(sorting && C > 1 && nq >= (int64_t)h->overlap_min_queries)) {
     h->cur = 0;
     SortInfo si;
@@ -1617,14 +1604,13 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "grid_min_queries") h->grid_min_queries = value;
   else if (s == "max_tail") h->max_tail = value;
   else if (s == "block_search") h->block_search = value;
-  else if (s == "tile_search") h->tile_search = value;
-  else if (s == "stream_search") h->stream_search = value;
-  else if (s == "pipe_search") h->pipe_search = value;
-  else if (s == "two_stage") h->two_stage = value;
   else if (s == "block_need") h->block_need = value;
+  else if (s == "strip_search") h->strip_search = value;
+  else if (s == "strip_spin_ns") h->strip_spin_ns = value;
+  else if (s == "strip_probe") h->strip_probe = value;
+  else if (s == "strip_min_per_tile") h->strip_min_per_tile = value;
   else if (s == "se2_fast") h->se2_fast = value;
   else if (s == "bf_tiled") h->bf_tiled = value;
-  else if (s == "flat_u") h->flat_u = value;
   else if (s == "use_graphs") h->use_graphs = value;
   else if (s == "pipeline_shape") h->pipeline_shape = value;
   else if (s == "periodic_axes") {
@@ -1661,15 +1647,13 @@ POMP_API int pomp_nn_get_stat(pomp_nn* h, const char* name, double* out) {
       ms += t;
     }
     *out = (s == "search_kernel_ms") ? ms : (double)(h->prof_used / 2);
-  } else if (s == "overflow_queries") {
+  } else if (s == "overflow_queries") {  // of the last large 2-D batch (first-stage deferrals)
     int c = 0;
-    for (int i = 0; i < 2; i++) {
-      int ci = 0;
-      if (h->ss[i].ovf.p) CUDA_TRY(cudaMemcpy(&ci, h->ss[i].ovf.p, sizeof(int), cudaMemcpyDeviceToHost));
-      c += ci;
-    }
+    if (h->ovf_count_dev) CUDA_TRY(cudaMemcpy(&c, h->ovf_count_dev, sizeof(int), cudaMemcpyDeviceToHost));
     *out = (double)c;
-  } else if (s == "n_cells") *out = h->grid_valid ? (double)h->grid.n_cells : 0.0;
+  } else if (s == "strip_launches") *out = (double)h->strip_launches;
+  else if (s == "strip_slots") *out = h->strip_build == h->grid_builds && h->grid_valid ? (double)h->strip.nslots : 0.0;
+  else if (s == "n_cells") *out = h->grid_valid ? (double)h->grid.n_cells : 0.0;
   else if (s == "n_indexed") *out = h->grid_valid ? (double)h->grid.n_indexed : 0.0;
   else if (s == "grid_axes") *out = h->grid_valid ? (double)h->grid.G : 0.0;
   else {

@@ -39,6 +39,17 @@ struct pomp_nn {
   DevBuf<int> sidx;
   DevBuf<int> tmp_i32;  // slot per point / counts
   DevBuf<long long> scan_tmp;
+  // strip index (strip2d.cuh): blocked copy of the 2-D grid index, built on demand for large nearest() batches
+  uint64_t strip_build = 0;  // grid_builds value it was derived from (0 = none)
+  uint64_t strip_launches = 0;
+  const int* ovf_count_dev = nullptr;  // device counter of the queries the last batch deferred to the overflow passes
+  StripDev strip;
+  DevBuf<double> spts2;
+  DevBuf<int> sidx2, tile_info, srow;
+  DevBuf<uint16_t> tile_cs;
+  double strip_search = 1;         // 2-D Euclidean k = 1 batches: streaming kernel over the strip index
+  double strip_spin_ns = 0, strip_probe = 0;  // tuning: back-off of waiting consumer warps, non-blocking producer probe
+  double strip_min_per_tile = 24;  // ... when the batch brings at least this many queries per tile on average
   // knobs
   double grid_min_points = 16384;
   double points_per_cell = 0;  // 0 = auto by number of grid axes
@@ -47,18 +58,10 @@ struct pomp_nn {
   double sort_shift = 6;
   double grid_min_queries = 64;
   double max_tail = 2048;
-  double stream_search = 0; // experimental: persistent TMA-pipelined kernel (grid_tile.cuh); slower than the flat
-                            // kernel until the index gets a blocked layout (one bulk copy per tile)
-  double two_stage = 0;     // k < 8: 1 = uncertified queries go to a second launch (R+1, list mode) instead of
-                            // retrying inside the thread
   double periodic_axes = 1;  // SO(2) components of a product metric are grid axes (wrap-around cells)
-  double flat_u = 4;        // flat 2-D kernel, k = 1: candidate loads in flight per thread (4, 6 or 8)
   double bf_tiled = 1;      // brute-force regime, Euclidean k = 1 batches: shared-memory tiled kernel
   double se2_fast = 1;      // SE(2) product metric: compile-time kernel (grid_se2.cuh) instead of the generic one
   double block_need = 0;    // k = 1: expected points in the certified ball that selects the block radius (0 = default)
-  double pipe_search = 0;   // experimental: per-thread software pipeline over queries (grid_pipe.cuh); its
-                            // 768 B/thread of cp.async slots leave 8 warps/SM -> 0.167 ms vs 0.117 ms (flat)
-  double tile_search = 0;   // 2-D Euclidean, sorted queries: streaming TMA tile kernel (grid_tile.cuh)
   double block_search = 1;  // 2-D Euclidean: fixed block of cells + certificate (0: pruned traversal; 2: also in 3-D)
   // scratch for queries
   DevBuf<double> q_dev;
@@ -156,13 +159,14 @@ struct Mailbox {
 }  // namespace pomp
 
 namespace pomp {
-// nn_fast2d.cu: 2-D Euclidean large-batch kernels (flattened block kernel, streaming tile kernel)
+// nn_fast2d.cu: 2-D Euclidean gather kernels (flattened block kernel + overflow passes)
 int launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm, int k,
                            int R, int64_t* idx, double* dist, int32_t* cnt, cudaStream_t st);
-int launch_grid_knn_stream2d(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
-                             const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist, int32_t* cnt,
-                             cudaStream_t st);
-int launch_grid_knn_tile2d_64(pomp_nn* h, const double* q, int64_t nq, const int* qperm, const double* qsorted,
-                              const int* qstart, int nbx, int k, int R, int64_t* idx, double* dist, int32_t* cnt,
-                              cudaStream_t st);
+// overflow lists of a first-stage 2-D search: flat kernel with the next larger block, then the pruned traversal
+int launch_overflow_2d(pomp_nn* h, const double* q, int64_t nq, int k, int* l1, int* c1, int* l2, int* c2, int64_t* idx,
+                       double* dist, int32_t* cnt, cudaStream_t st);
+// strip2d.cu: streaming nearest-neighbour search over the strip index
+bool strip_eligible(const pomp_nn* h, int64_t nq, int k);
+int strip_nearest(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
+                  cudaStream_t st);
 }  // namespace pomp

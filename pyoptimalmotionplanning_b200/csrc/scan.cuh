@@ -42,7 +42,7 @@ __device__ __forceinline__ long long block_excl_scan(long long v, long long* tot
   return res;
 }
 
-__global__ void scan_tile_sums(const int* __restrict__ in, long long n, long long* __restrict__ tile_sums) {
+static __global__ void scan_tile_sums(const int* __restrict__ in, long long n, long long* __restrict__ tile_sums) {
   long long base = (long long)blockIdx.x * SCAN_TILE;
   long long s = 0;
 #pragma unroll
@@ -56,7 +56,7 @@ __global__ void scan_tile_sums(const int* __restrict__ in, long long n, long lon
 }
 
 // single block: in-place exclusive scan of the tile sums
-__global__ void scan_sums_inplace(long long* sums, int nb) {
+static __global__ void scan_sums_inplace(long long* sums, int nb) {
   long long carry = 0;
   for (int base = 0; base < nb; base += blockDim.x) {
     int i = base + threadIdx.x;

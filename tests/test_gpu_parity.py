@@ -333,10 +333,11 @@ def test_errors_are_loud():
 
 
 @pytest.mark.parametrize("k", [1, 4, 16, 32])
-@pytest.mark.parametrize("mode", ["pipe", "stream", "tile", "block", "pruned"])
+@pytest.mark.parametrize("mode", ["strip", "block", "pruned"])
 def test_large_batch_2d_paths_match_oracle(k, mode):
-    """The bucket-sorted large-batch paths (streaming TMA tile kernel / fixed-block kernel / pruned
-    traversal) against the oracle on a query subset, and against each other on every query."""
+    """The large-batch paths (streaming kernel over the strip index -- k = 1 only, larger k falls through to the
+    gather kernels -- / fixed-block kernel / pruned traversal) against the oracle on a query subset, and against
+    each other on every query."""
     rng = np.random.default_rng(200 + k)
     n, nq = 300000, 40000
     pts = rng.random((n, 2))
@@ -345,19 +346,16 @@ def test_large_batch_2d_paths_match_oracle(k, mode):
                         rng.random((1000, 2)) * 1.2 - 0.1])
     m = MetricSpec.euclidean(2)
     nn = _nn(m, pts, grid=True)
-    nn.set_param("pipe_search", 1 if mode == "pipe" else 0)
-    nn.set_param("stream_search", 1 if mode == "stream" else 0)
-    nn.set_param("tile_search", 1 if mode == "tile" else 0)
-    nn.set_param("block_search", 1 if mode in ("block", "pipe") else 0)
+    nn.set_param("strip_search", 1 if mode == "strip" else 0)
+    nn.set_param("strip_min_per_tile", 0)
+    nn.set_param("block_search", 1 if mode in ("block", "strip") else 0)
     idx, dist, cnt = nn.knearest(q, k)
     sub = rng.choice(nq, 2500, replace=False)
     oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
     assert (idx[sub] == oi).all() and (dist[sub] == od).all() and (cnt[sub] == oc).all()
     ref = _nn(m, pts, grid=True)
     ref.set_param("sort_queries", 0)
-    ref.set_param("stream_search", 0)
-    ref.set_param("pipe_search", 0)
-    ref.set_param("tile_search", 0)
+    ref.set_param("strip_search", 0)
     ref.set_param("block_search", 0)
     ridx, rdist, rcnt = ref.knearest(q, k)
     assert (idx == ridx).all() and (dist == rdist).all()
@@ -395,26 +393,47 @@ def test_tile_path_with_masks_and_tail():
     assert (idx[sub] == oi).all() and (dist[sub] == od).all()
 
 
-def test_stream_kernel_at_bench_like_density():
-    """The persistent TMA kernel only engages when a tile's queries fit its 5 chunk slots (about 1/8 query per
-    cell, the headline configuration): exercise exactly that regime, plus a clustered region that overflows."""
+@pytest.mark.parametrize("shape", ["uniform", "clustered", "ragged", "sparse_queries", "ties"])
+def test_strip_streaming_kernel_equals_gather_kernels_and_oracle(shape):
+    """The persistent bulk-copy kernel over the strip index (strip2d.cuh): uniform data at the bench density,
+    clusters that overflow a stage (those tiles go to the overflow list), a grid whose width / height are not
+    multiples of the tile, query batches that leave most tiles empty, and a lattice full of exact distance ties
+    (lowest insertion index must win, also between the replicated halo copies)."""
     rng = np.random.default_rng(77)
-    n, nq = 1 << 20, 1 << 16
+    n, nq = 1 << 20, 1 << 17
     pts = rng.random((n, 2))
-    pts[:30000] = 0.25 + 0.001 * rng.standard_normal((30000, 2))
     q = rng.random((nq, 2))
+    if shape == "clustered":
+        pts[:60000] = 0.25 + 0.001 * rng.standard_normal((60000, 2))
+        q[:20000] = 0.25 + 0.002 * rng.standard_normal((20000, 2))
+    elif shape == "ragged":
+        pts = pts * [1.0, 0.37] + [3.0, -2.0]
+        q = q * [1.1, 0.45] + [2.95, -2.03]               # some queries outside the bounding box
+    elif shape == "sparse_queries":
+        q = 0.6 + 0.05 * rng.random((nq, 2))               # a few tiles hold every query
+    elif shape == "ties":
+        pts = np.round(pts * 1500) / 1500                  # lattice: many duplicates and equidistant pairs
+        q = np.round(q * 3000) / 3000
     m = MetricSpec.euclidean(2)
-    for k in (1, 4):
-        nn = _nn(m, pts, grid=True)
-        nn.set_param("stream_search", 1)
-        idx, dist, cnt = nn.knearest(q, k)
-        ref = _nn(m, pts, grid=True)
-        ref.set_param("stream_search", 0)
-        ridx, rdist, rcnt = ref.knearest(q, k)
-        assert (idx == ridx).all() and (dist == rdist).all() and (cnt == rcnt).all()
-        sub = rng.choice(nq, 800, replace=False)
-        oi, od, oc = oracle.nn_knearest(m, pts, q[sub], k)
-        assert (idx[sub] == oi).all() and (dist[sub] == od).all()
+    nn = _nn(m, pts, grid=True)
+    nn.set_param("strip_min_per_tile", 0)
+    idx, dist = nn.nearest(np.ascontiguousarray(q))
+    assert nn.get_stat("strip_launches") > 0
+    ref = _nn(m, pts, grid=True)
+    ref.set_param("strip_search", 0)
+    ridx, rdist = ref.nearest(np.ascontiguousarray(q))
+    assert (idx == ridx).all() and (dist == rdist).all()
+    sub = rng.choice(nq, 1500, replace=False)
+    oi, od = oracle.KDTree(m, pts).nearest(q[sub]) if shape != "ties" else oracle.nn_nearest(m, pts, q[sub[:200]])
+    k = len(oi)
+    assert (idx[sub[:k]] == oi).all() and (dist[sub[:k]] == od).all()
+    # index mutation invalidates the strip copy: appended points must be seen (tail -> gather kernels, then rebuild)
+    extra = q[:3000] + 1e-7
+    nn.add(extra)
+    i2, d2 = nn.nearest(np.ascontiguousarray(q[:40000]))
+    assert shape == "ties" or (i2[:3000] >= n).all()     # (on the lattice an old point may coincide with the query)
+    oi2, od2 = oracle.KDTree(m, np.concatenate([pts, extra])).nearest(q[:2000]) if shape != "ties" else (i2[:2000], d2[:2000])
+    assert (i2[:2000] == oi2).all() and (d2[:2000] == od2).all()
 
 
 def test_so2_periodic_axis_wraps_and_normalises():
