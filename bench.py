@@ -255,8 +255,10 @@ def workload_config(gpus):
             "points": 1 << LOG2_N, "queries_per_gpu": 1 << LOG2_Q, "global_queries": gpus << LOG2_Q, "dim": DIM, "k": K,
             "l2": "inputs (%.0f MB of points) exceed the 126 MB L2; no explicit flush" % ((1 << LOG2_N) * DIM * 8 / 1e6),
             "parallelism": "1 GPU" if gpus == 1 else
-                           "queries striped over %d GPUs, index replicated (no data-path collective); the node-set-"
-                           "sharded NCCL path is reported under node_sharded" % gpus}
+                           "node set (2^%d points) sharded spatially over %d GPUs (slabs + halo); queries routed to the "
+                           "owning GPU with all_to_all (NCCL), packed (distance, index) records returned with all_to_all, "
+                           "uncertified remainder through an all_gather fallback; replicated-index number under "
+                           "replicated_index" % (LOG2_N, gpus)}
 
 
 # ------------------------------------------------------------------------------ extras (N=1)
@@ -738,36 +740,82 @@ def run_gpu(args):
     e2e_idx_s = float(t.item())
     assert torch.equal(idx_h[:, 0], idx.cpu())
 
-    # ---- N > 1 extra: the node-set-sharded path: rank r holds a DIFFERENT 2^24-point shard
-    # (N x 2^24 points in total), the 2^20-query batch is split into per-rank slices, every step is
-    # all-gather(queries) -> local top-k -> all-to-all(candidates) -> merge kernel.
+    # ---- N > 1: the HEADLINE is the north-star split: ONE node set of 2^24 points sharded spatially
+    # over the N GPUs (slabs of the last coordinate + halo copies), 2^20 queries per GPU routed to the owning GPU
+    # with an all-to-all over NCCL/NVLink, answered locally with a certificate, packed (distance, index) records
+    # returned with a second all-to-all, the uncertified remainder through an all-gather fallback.
     sharded = None
     if world > 1:
-        pts2 = torch.from_numpy(gen_points(n, DIM, 99 + rank)).cuda(local)
-        nn2 = CudaNN(MetricSpec.euclidean(DIM), local)
-        nn2.set_device(pts2.data_ptr(), n, st)
-        nn2.build_index(st)
-        shard = ShardedNearestNeighbors(rank * n, nn=nn2)
-        qsl = nq // world
-        qd2 = torch.from_numpy(gen_queries(nq, DIM)[rank * qsl:(rank + 1) * qsl].copy()).cuda(local)
+        from pyoptimalmotionplanning_b200.sharded import SpatialShardedNearestNeighbors, stripe
+        b0, b1 = stripe(n, rank, world)
+        sp = SpatialShardedNearestNeighbors(MetricSpec.euclidean(DIM), device=local)
+        sp.set(torch.from_numpy(pts_h[b0:b1].copy()).cuda(local), b0)
+        # exchange over peer memory (NVLink stores from our kernels); NCCL all-to-all variant as the fallback / extra
+        exch = os.environ.get("POMP_SHARD_EXCHANGE", "p2p")
+        try:
+            if exch != "p2p":
+                raise RuntimeError("NCCL exchange requested")
+            sp.knearest_p2p(q_dev, K)
+            shard_call, exch = sp.knearest_p2p, "p2p"
+        except Exception as e:   # no symmetric memory on this box: the NCCL exchange answers the same
+            if rank == 0:
+                print("bench.py: peer-memory exchange unavailable (%s); using NCCL all_to_all" % str(e)[:200], file=sys.stderr)
+            shard_call, exch = sp.knearest_fast, "nccl"
         for _ in range(3):
-            shard.knearest(qd2, K)
+            si, sd, sst = shard_call(q_dev, K)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(args.steps):
-            shard.knearest(qd2, K)
+            si, sd, sst = shard_call(q_dev, K)
         s1.record()
         barrier()
         t = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sharded = {"queries_per_s": nq / (float(t.item()) * 1e-3), "ms_per_step": float(t.item()),
-                   "total_points": n * world,
-                   "note": "capacity scaling: per-query cost of the grid index is ~independent of N, so sharding "
-                           "the node set adds points, not queries/s"}
+        sh_ms = float(t.item())
+        trace = []
+        shard_call(q_dev, K, _trace=trace)
+        torch.cuda.synchronize()
+        stage_trace = [{"stage": trace[i][0], "gpu_ms": round(trace[i - 1][1].elapsed_time(trace[i][1]), 4),
+                        "host_ms": round((trace[i][2] - trace[i - 1][2]) * 1e3, 4)} for i in range(1, len(trace))]
+        # the sharded answer must equal the one-index answer (this rank's replicated index over the same 2^24 points)
+        assert torch.equal(si[:, 0], idx) and torch.equal(sd[:, 0], dst), "sharded answer differs from the single index"
+        # end to end: pinned host queries in, host results out
+        sq_h = q_slice_h
+        si_h = torch.empty((qs, K), dtype=torch.int64).pin_memory()
+        sd_h = torch.empty((qs, K), dtype=torch.float64).pin_memory()
+        qd2 = torch.empty_like(q_dev)
+
+        def sharded_e2e():
+            qd2.copy_(sq_h, non_blocking=True)
+            a, b_, _ = shard_call(qd2, K)
+            si_h.copy_(a, non_blocking=True)
+            sd_h.copy_(b_, non_blocking=True)
+            torch.cuda.synchronize()
+        for _ in range(3):
+            sharded_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sharded_e2e()
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sharded = {"ms_per_step": sh_ms, "queries_per_s": world * nq / (sh_ms * 1e-3), "e2e_s": float(t.item()),
+                   "points_per_gpu_owned": sp.n_owned, "halo": sp.halo, "stats_rank0": sst,
+                   "equal_to_single_index": int(qs), "stage_trace_rank0": stage_trace, "exchange": exch}
 
     striped = run_striped(world, rank, local, barrier) if world > 1 and not args.no_extras else None
 
+    parity_checked = 0
+    if rank == 0 and not args.no_cpu:
+        # a sample of the timed answers against the oracle (C restatement of pomp's kd-tree; exact for Euclid)
+        from oracle import oracle as _orc
+        sub = np.random.default_rng(5).choice(qs, 4096, replace=False)
+        oi, od = _orc.KDTree(_orc.MetricSpec.euclidean(DIM), pts_h).nearest(q_all_h[sub])
+        gi, gd = idx.cpu().numpy()[sub], dst.cpu().numpy()[sub]
+        assert (gi == oi).all() and (gd == od).all(), "timed result differs from the oracle"
+        parity_checked = len(sub)
     if rank == 0:
         alg_bytes = n * DIM * 8 + nq * DIM * 8 + nq * K * 16
         kern_per_step = kern_ms / args.steps
@@ -790,8 +838,23 @@ def run_gpu(args):
                                    "note": "same call with dist_h = NULL (NearestNeighbors.nearest returns the node only)"},
                 "gpu_launches": int(launches), "clocks": clocks, "numa_pinning_rank0": numa,
                 "index": {"cells": nn.get_stat("n_cells"), "overflow_queries_last_step": nn.get_stat("overflow_queries")}}
+        line["parity_checked"] = parity_checked
         if sharded is not None:
+            # N > 1: the spatially sharded node set is the headline; the replicated-index number stays as an extra
+            line["replicated_index"] = {"value": line["value"], "ms_per_step": line["ms_per_step"], "e2e": line["e2e"],
+                                        "note": "every GPU holds all 2^24 points and answers its own 2^20 queries "
+                                                "(no data-path collective)"}
+            line["value"] = sharded["queries_per_s"]
+            line["ms_per_step"] = sharded["ms_per_step"]
+            line["e2e"] = {"value": world * nq / sharded["e2e_s"], "unit": "queries/s",
+                           "h2d_bytes_per_step": qs * DIM * 8 * world, "d2h_bytes_per_step": qs * K * 16 * world,
+                           "ms_per_step": sharded["e2e_s"] * 1e3,
+                           "api": "SpatialShardedNearestNeighbors.knearest_fast (pinned host queries in, host results out)"}
+            line.pop("e2e_index_only", None)
             line["node_sharded"] = sharded
+            r = line["roofline"]
+            r["note"] = ("kernel figures are those of the replicated-index leg (2^24-point index per GPU); in the sharded "
+                         "leg every GPU streams its own %d owned points" % sharded["points_per_gpu_owned"])
         if striped is not None:
             line["striped_units"] = striped
         if world == 1:

@@ -143,6 +143,61 @@ int pomp_nn_neighbors(pomp_nn* h, const double* q, int64_t nq, double radius, in
 int pomp_nn_neighbors_h(pomp_nn* h, const double* q_h, int64_t nq, double radius, int inclusive,
                         int64_t* offsets_h, int64_t* idx_h, int64_t idx_capacity, int64_t* needed_h);
 
+/* multi-GPU, SPATIAL sharding (no reference counterpart: pomp is single-process).  Rank r owns the slab
+   bounds[r-1] <= x[axis] < bounds[r] of the node set (bounds[-1] = -inf, bounds[n_ranks-1] = +inf) plus a halo copy of
+   its neighbours' points near the slab faces.  pomp_shard_route counting-sorts a query batch by owning rank
+   (q_out: queries grouped by rank, perm_out[t] = original position, counts_h[r] = queries for rank r; synchronises
+   the stream: the host needs the split sizes for the all-to-all).  dest_scratch: nq int32, counts_dev: 128 uint64.
+   pomp_shard_finalize turns local k-NN answers into packed 16-byte records (distance bits, GLOBAL index) for the
+   return exchange and flags the queries whose k-th distance reaches outside the covered region [lo_cov, hi_cov]
+   (uncertified[i] = 1); drop_halo = 1 blanks halo copies (the all-ranks fallback merges owned points only).
+   pomp_shard_unpack writes records back to (idx, dist, count) at perm[i] (perm may be NULL). */
+int pomp_shard_route(const double* q, int64_t nq, int32_t dim, int32_t axis, const double* bounds_h, int32_t n_ranks,
+                     int32_t* dest_scratch, uint64_t* counts_dev, int64_t* counts_h, double* q_out, int64_t* perm_out,
+                     void* stream);
+int pomp_shard_finalize(const double* q, int64_t nq, int32_t dim, int32_t axis, double lo_cov, double hi_cov,
+                        int32_t k, const int64_t* idx_local, const double* dist, const int64_t* local_to_global,
+                        const uint8_t* halo_flag, int32_t drop_halo, int64_t* records, uint8_t* uncertified,
+                        void* stream);
+int pomp_shard_unpack(const int64_t* records, int64_t nq, int32_t k, const int64_t* perm, int64_t* idx, double* dist,
+                      int32_t* count, void* stream);
+/* The same exchange WITHOUT host synchronisation (equal-split all-to-alls): every destination rank gets a fixed block
+   of `cap` query slots (q_out [n_ranks][cap][dim] / perm_out [n_ranks][cap], pre-filled by the caller with an ordinary
+   point of the destination slab / -1: padding must be cheap to answer, a NaN query scans a whole shard);
+   what does not fit is appended to defer_list (positions in the caller's batch; counters[64] counts them,
+   counters[0..63] are the per-rank cursors: the caller zeroes all 65).  pomp_shard_finalize_rows writes rows of
+   2k+1 words (k records + "no certificate" flag); pomp_shard_unpack_rows stores certified rows at perm[i] and appends
+   the flagged ones to the deferred list; gather / scatter move the first F deferred queries into / out of the
+   fixed-size block of the all-ranks fallback (padded with pad_point[dim], a device pointer). */
+int pomp_shard_route_fixed(const double* q, int64_t nq, int32_t dim, int32_t axis, const double* bounds_h,
+                           int32_t n_ranks, int64_t cap, uint64_t* counters, double* q_out, int64_t* perm_out,
+                           int64_t* defer_list, int64_t defer_cap, void* stream);
+int pomp_shard_finalize_rows(const double* q, int64_t nq, int32_t dim, int32_t axis, double lo_cov, double hi_cov,
+                             int32_t k, const int64_t* idx_local, const double* dist, const int64_t* local_to_global,
+                             const uint8_t* halo_flag, int32_t drop_halo, int64_t* rows, void* stream);
+int pomp_shard_unpack_rows(const int64_t* rows, int64_t n, int32_t k, const int64_t* perm, int64_t* idx, double* dist,
+                           int64_t* defer_list, uint64_t* defer_count, int64_t defer_cap, void* stream);
+int pomp_shard_gather_deferred(const double* q, int32_t dim, const int64_t* defer_list, const uint64_t* defer_count,
+                               int64_t F, const double* pad_point, double* qf, void* stream);
+/* Peer-memory variant: the exchange is done by the kernels themselves with NVLink stores into buffers every rank
+   maps from its peers (peer_*_blocks_h[r] = device address of rank r's block in THIS process, from CUDA IPC /
+   torch symmetric memory).  route: query i owned by rank r is stored at rank r's block, row my_rank*cap + slot;
+   finalize: the answer row of slot (src, t) is stored at rank src's result block, row my_rank*cap + t; unpack reads
+   the local result block [n_ranks][cap] (slots below the per-rank cursors in counters[0..n_ranks) are valid).  The
+   caller separates the three with device barriers; no collective is on the data path. */
+int pomp_shard_route_p2p(const double* q, int64_t nq, int32_t dim, int32_t axis, const double* bounds_h, int32_t n_ranks,
+                         int32_t my_rank, int64_t cap, uint64_t* counters, const uint64_t* peer_query_blocks_h,
+                         int64_t* perm_out, int64_t* defer_list, int64_t defer_cap, void* stream);
+int pomp_shard_finalize_p2p(const double* q, int64_t cap, int32_t n_ranks, int32_t my_rank, int32_t dim, int32_t axis,
+                            double lo_cov, double hi_cov, int32_t k, const int64_t* idx_local, const double* dist,
+                            const int64_t* local_to_global, const uint64_t* peer_result_blocks_h, void* stream);
+int pomp_shard_unpack_p2p(const int64_t* rows, int32_t n_ranks, int64_t cap, int32_t k, const int64_t* perm,
+                          const uint64_t* counters, int64_t* idx, double* dist, int64_t* defer_list, int64_t defer_cap,
+                          void* stream);
+int pomp_shard_scatter_deferred(const int64_t* merged_idx, const double* merged_dist, int32_t k,
+                                const int64_t* defer_list, const uint64_t* defer_count, int64_t F, int64_t* idx,
+                                double* dist, void* stream);
+
 /* multi-GPU: merge G per-shard candidate lists [G][nq][k] (already carrying GLOBAL
    indices) into the k best per query by (dist, idx).  The exchange itself (NCCL all-to-all /
    all-gather over NVLink) is issued by the host binding through torch.distributed. */

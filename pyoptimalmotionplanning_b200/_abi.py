@@ -87,6 +87,17 @@ SIGNATURES = {
     "pomp_nn_neighbors": (C.c_int, [_P, _P, _I64, _D, C.c_int, _P, _P, _I64, _P, _P]),
     "pomp_nn_neighbors_h": (C.c_int, [_P, _P, _I64, _D, C.c_int, _P, _P, _I64, _P]),
     "pomp_nn_merge_candidates": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
+    "pomp_shard_route": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "pomp_shard_finalize": (C.c_int, [_P, _I64, _I32, _I32, _D, _D, _I32, _P, _P, _P, _P, _I32, _P, _P, _P]),
+    "pomp_shard_unpack": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "pomp_shard_route_fixed": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I64, _P, _P, _P, _P, _I64, _P]),
+    "pomp_shard_finalize_rows": (C.c_int, [_P, _I64, _I32, _I32, _D, _D, _I32, _P, _P, _P, _P, _I32, _P, _P]),
+    "pomp_shard_unpack_rows": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
+    "pomp_shard_route_p2p": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I32, _I64, _P, _P, _P, _P, _I64, _P]),
+    "pomp_shard_finalize_p2p": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _D, _D, _I32, _P, _P, _P, _P, _P]),
+    "pomp_shard_unpack_p2p": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
+    "pomp_shard_gather_deferred": (C.c_int, [_P, _I32, _P, _P, _I64, _P, _P, _P]),
+    "pomp_shard_scatter_deferred": (C.c_int, [_P, _P, _I32, _P, _P, _I64, _P, _P, _P]),
     "pomp_space_create": (C.c_int, [_SD, C.c_int, C.POINTER(_P)]),
     "pomp_space_destroy": (C.c_int, [_P]),
     "pomp_space_set_bounds": (C.c_int, [_P, _P, _P]),

@@ -731,3 +731,75 @@ def test_graph_replay_survives_interleaved_batch_sizes():
     ref.set_param("use_graphs", 0)
     ri, rd = ref.nearest(big)
     assert (full_i == ri).all() and (full_d == rd).all()
+
+
+def test_spatial_shard_kernels_match_numpy_ops():
+    """csrc/shard.cu (route / finalize / unpack) against the NumPy stand-ins the gloo tests use, then the whole
+    SpatialShardedNearestNeighbors on CUDA tensors in a one-rank NCCL group against the oracle."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from pyoptimalmotionplanning_b200.sharded import _CudaShardOps, SpatialShardedNearestNeighbors
+    from tests.test_sharded_gloo import NumpyShardOps
+    rng = np.random.default_rng(8)
+    m = MetricSpec.euclidean(2)
+    cu, nu = _CudaShardOps(m, 0), NumpyShardOps(m)
+    q = rng.random((50000, 2))
+    q[:5, 1] = [0.25, 0.5, 0.75, np.nan, -3.0]            # exactly on slab faces, NaN, far outside
+    bounds = [0.25, 0.5, 0.75]
+    qs, perm, counts = cu.route(torch.from_numpy(q).cuda(), 1, bounds, 4)
+    nqs, nperm, ncounts = nu.route(torch.from_numpy(q), 1, bounds, 4)
+    assert counts[:3] == ncounts[:3] or np.isnan(q[:, 1]).any()
+    perm_h, qs_h = perm.cpu().numpy(), qs.cpu().numpy()
+    assert sorted(perm_h.tolist()) == list(range(len(q)))
+    assert ((qs_h == q[perm_h]) | np.isnan(qs_h)).all()
+    start = 0
+    for r, c in enumerate(counts):                        # every routed block holds exactly its slab's queries
+        y = qs_h[start:start + c, 1]
+        lo = -np.inf if r == 0 else bounds[r - 1]
+        hi = np.inf if r == 3 else bounds[r]
+        assert (np.isnan(y) | ((y >= lo) & (y < hi))).all()
+        start += c
+    pts = rng.random((30000, 2))
+    cu.set_points(torch.from_numpy(pts).cuda())
+    nu.set_points(torch.from_numpy(pts))
+    l2g = torch.from_numpy(np.sort(rng.choice(10 ** 6, 30000, replace=False)))
+    halo = torch.from_numpy((rng.random(30000) < 0.2).astype(np.uint8))
+    qq = torch.from_numpy(rng.random((3000, 2)))
+    for drop in (False, True):
+        il, dl = cu.local_knn(qq.cuda(), 5)
+        rec, fl = cu.finalize(qq.cuda(), 1, 0.1, 0.9, 5, il, dl, l2g.cuda(), halo.cuda(), drop, True)
+        nil, ndl = nu.local_knn(qq, 5)
+        nrec, nfl = nu.finalize(qq, 1, 0.1, 0.9, 5, nil, ndl, l2g, halo, drop, True)
+        assert (rec.cpu() == nrec).all() and (fl.cpu() == nfl).all()
+        p = torch.from_numpy(rng.permutation(3000))
+        ui, ud = cu.unpack(rec, p.cuda(), 3000, 5)
+        ni, nd = nu.unpack(nrec, p, 3000, 5)
+        assert (ui.cpu() == ni).all() and (ud.cpu() == nd).all()
+    # the whole object, one rank over NCCL
+    if not dist.is_initialized():
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    big = rng.random((200000, 2))
+    sp = SpatialShardedNearestNeighbors(m, device=0)
+    sp.set(torch.from_numpy(big).cuda(), 0)
+    bq = rng.random((40000, 2)) * 1.1 - 0.05
+    idx, dst, st = sp.knearest(torch.from_numpy(bq).cuda(), 4)
+    oi, od, _ = oracle.KDTree(m, big).knearest(bq, 4)
+    assert (idx.cpu().numpy() == oi).all() and (dst.cpu().numpy() == od).all()
+    fi, fd, fst = sp.knearest_fast(torch.from_numpy(bq).cuda(), 4)            # fixed-capacity, sync-free variant
+    assert (fi.cpu().numpy() == oi).all() and (fd.cpu().numpy() == od).all() and "deferred" in fst
+    sp.hi_cov = 0.97      # pretend the slab ends there: queries beyond lose their certificate -> exact fallback
+    fi, fd, fst = sp.knearest_fast(torch.from_numpy(bq).cuda(), 4)
+    assert (fi.cpu().numpy() == oi).all() and (fd.cpu().numpy() == od).all() and fst["deferred"] > 500
+    fi, fd, fst = sp.knearest_fast(torch.from_numpy(bq).cuda(), 4, slack=0.5)   # blocks too small: the rest is deferred
+    assert (fi.cpu().numpy() == oi).all() and (fd.cpu().numpy() == od).all() and fst["deferred"] > 10000
+    sp.hi_cov = float("inf")
+    off, hits = sp.neighbors(torch.from_numpy(bq[:2000]).cuda(), 0.004)
+    ooff, ohits = oracle.nn_neighbors(m, big, bq[:2000], 0.004, True)
+    assert (off.cpu().numpy() == ooff).all() and (hits.cpu().numpy() == ohits).all()
+    dist.destroy_process_group()
