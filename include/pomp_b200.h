@@ -372,6 +372,35 @@ int pomp_forest_extend_multi_h(pomp_forest* f, pomp_space* s, int32_t n_iters, c
                                int32_t* n_done_h, int64_t* parent_h, double* xnew_h, double* edge_len_h,
                                int32_t* added_h);
 
+/* ---------------------------------------------------------------- lock-step sst* forest ------------------ */
+/* n_trials independent StableSparseRRT trials (rrtstarplanner.py:203-410 under the restart schedule of
+   StableSparseRRTStar :454-471), one block per trial, n_iters planner iterations per call.  The caller supplies, per
+   trial and iteration, what the reference draws from Python's `random` (sample xrand[x_dim], control u[u_dim] =
+   (duration, base control), valid = controlSet.contains(u)) and the per-iteration selection / witness radii and
+   restart flags (restart[m] = 1: the tree is reset to the root BEFORE iteration m; restart_now: before the first).
+   On the device: pickNode, the stepwise trajectory of `dyn` as a piecewise-linear edge under `geodesic`, the sampled
+   edge check against `space`, costs (+ u[0]), witness bookkeeping, pruning, goal test (geodesic distance to
+   goal_center <= goal_radius; goal_center NULL = none).  Outputs per trial: best goal cost so far (+inf = none),
+   nodes created since the last restart, iterations in which no active node existed (must be 0 for the pre-drawn
+   random stream to stay in step).  POMP_ERR_CAPACITY when an arena overflows.
+   half_sq_last_h[trial][iter] / half_sq_full (constant-acceleration steps, statespace.py:55-59): the caller's
+   0.5*dt**2 for the last (partial) and for a full integration step -- Python's ** is libm pow, which differs from
+   dt*dt in ~0.1 % of inputs, and one ulp in a node coordinate is a different tree; NULL: computed on the device. */
+typedef struct pomp_sst pomp_sst;
+int pomp_sst_create(int32_t x_dim, int32_t u_dim, int32_t n_trials, int32_t node_capacity, int32_t witness_capacity,
+                    const pomp_dyn_desc* dyn, const pomp_metric_desc* geodesic, int device, pomp_sst** out);
+int pomp_sst_destroy(pomp_sst* f);
+int pomp_sst_reset_h(pomp_sst* f, const double* root_h);
+int pomp_sst_step_h(pomp_sst* f, pomp_space* space, int32_t n_iters, const double* xrand_h, const double* u_h,
+                    const uint8_t* valid_h, const double* sel_radius_h, const double* wit_radius_h,
+                    const uint8_t* restart_h, int32_t restart_now, const double* goal_center_h, double goal_radius,
+                    double resolution, const double* half_sq_last_h, double half_sq_full, double* best_cost_h,
+                    int32_t* n_nodes_h, int32_t* n_none_h);
+/* node arrays of one trial in creation order (any output may be NULL): state, parent (-1: root / removed), alive
+   (still in the tree), cost, active; *count_h = nodes created since the last restart */
+int pomp_sst_get_trial_h(pomp_sst* f, int32_t trial, double* x_h, int32_t* parent_h, uint8_t* alive_h, double* cost_h,
+                         uint8_t* active_h, int32_t* count_h);
+
 #ifdef __cplusplus
 }
 #endif

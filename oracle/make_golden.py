@@ -410,6 +410,18 @@ def gen_planners():
         key = "G3_sststar_doubleintegrator" + ("" if seed == 7 else "_seed%d" % seed)
         out[key] = {"seed": seed, "iters": 1200, "num_nodes": len(V), "hash": roadmap_hash(V, E),
                     "best_cost": planner.bestPathCost}
+    # G3 forest: 16 seeded sst* trials (BASELINE config 5, "4096 independent seeded trials"), one reference run each
+    seeds = list(range(100, 116))
+    rows = []
+    for seed in seeds:
+        random.seed(seed)
+        prob = doubleintegrator.doubleIntegratorTest()
+        with contextlib.redirect_stdout(io.StringIO()):
+            planner = prob.planner("sst*", selectionRadius=0.3, witnessRadius=0.3)
+            planner.planMore(1000)
+        V, E = planner.getRoadmap()
+        rows.append([roadmap_hash(V, E), len(V), planner.bestPathCost])
+    out["G3_sststar_forest"] = {"seeds": seeds, "iters": 1000, "results": rows}
     random.seed(7)
     prob = dubins.dubinsCarTest()
     with contextlib.redirect_stdout(io.StringIO()):

@@ -98,6 +98,11 @@ SIGNATURES = {
     "pomp_shard_unpack_p2p": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "pomp_shard_gather_deferred": (C.c_int, [_P, _I32, _P, _P, _I64, _P, _P, _P]),
     "pomp_shard_scatter_deferred": (C.c_int, [_P, _P, _I32, _P, _P, _I64, _P, _P, _P]),
+    "pomp_sst_create": (C.c_int, [_I32, _I32, _I32, _I32, _I32, _P, _P, C.c_int, C.POINTER(_P)]),
+    "pomp_sst_destroy": (C.c_int, [_P]),
+    "pomp_sst_reset_h": (C.c_int, [_P, _P]),
+    "pomp_sst_step_h": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _D, _D, _P, _D, _P, _P, _P]),
+    "pomp_sst_get_trial_h": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P]),
     "pomp_space_create": (C.c_int, [_SD, C.c_int, C.POINTER(_P)]),
     "pomp_space_destroy": (C.c_int, [_P]),
     "pomp_space_set_bounds": (C.c_int, [_P, _P, _P]),

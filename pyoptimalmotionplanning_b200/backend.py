@@ -420,6 +420,63 @@ class CudaForest(object):
                                                             self.parent_m, self.xnew_m, self.elen_m, self.added_m))
 
 
+class CudaSSTForest(object):
+    """T lock-step sst* trials on one GPU (pomp_sst_* entry points, csrc/sst.cu); the host driver is sst.SSTStarForest."""
+
+    def __init__(self, x_dim, u_dim, n_trials, node_cap, witness_cap, dyn_spec, geodesic_spec, space_spec, device=0):
+        self.lib = _abi.load_library()
+        self.X, self.U, self.T, self.ncap = x_dim, u_dim, n_trials, node_cap
+        self.space = CudaSpace(space_spec, device)
+        self._h = C.c_void_p()
+        self._dyn, self._geo = dyn_spec.desc(), geodesic_spec.desc()
+        check(self.lib, self.lib.pomp_sst_create(x_dim, u_dim, n_trials, node_cap, witness_cap, C.byref(self._dyn),
+                                                 C.byref(self._geo), device, C.byref(self._h)))
+        self._best = np.empty(n_trials, np.float64)
+        self._nodes = np.empty(n_trials, np.int32)
+        self._none = np.empty(n_trials, np.int32)
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self.lib.pomp_sst_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, root):
+        r = _f64(root)
+        check(self.lib, self.lib.pomp_sst_reset_h(self._h, _ptr(r)))
+
+    def step(self, M, xr, uu, valid, sel, wit, restart, goal_c, goal_r, res, restart_now=False, half_sq=None):
+        """half_sq = (per-sample 0.5*dt_last**2 [T][M], 0.5*dt**2) computed by the caller with Python's ** (CV dynamics)."""
+        xr = _f64(xr)
+        uu = _f64(uu)
+        valid = np.ascontiguousarray(np.asarray(valid, dtype=np.uint8))
+        sel, wit = _f64(sel if M else [0.0]), _f64(wit if M else [0.0])
+        rs = np.ascontiguousarray(np.asarray(restart if M else [0], dtype=np.uint8))
+        gc = _f64(goal_c)
+        check(self.lib, self.lib.pomp_sst_step_h(self._h, self.space._h, int(M), _ptr(xr), _ptr(uu), _ptr(valid), _ptr(sel),
+                                                 _ptr(wit), _ptr(rs), 1 if restart_now else 0,
+                                                 _ptr(gc) if goal_r >= 0 else None, float(goal_r), float(res),
+                                                 _ptr(_f64(half_sq[0])) if (half_sq is not None and M) else None,
+                                                 float(half_sq[1]) if half_sq is not None else 0.0,
+                                                 _ptr(self._best), _ptr(self._nodes), _ptr(self._none)))
+        return self._best.copy(), self._nodes.copy(), self._none.copy()
+
+    def get_trial(self, trial):
+        cnt = C.c_int32()
+        x = np.empty((self.ncap, self.X), np.float64)
+        parent = np.empty(self.ncap, np.int32)
+        alive = np.empty(self.ncap, np.uint8)
+        check(self.lib, self.lib.pomp_sst_get_trial_h(self._h, int(trial), _ptr(x), _ptr(parent), _ptr(alive), None, None,
+                                                      C.byref(cnt)))
+        n = cnt.value
+        return x[:n].tolist(), parent[:n].tolist(), [bool(a) for a in alive[:n]]
+
+
 def launch_count():
     return _abi.load_library().pomp_launch_count()
 

@@ -4,6 +4,8 @@ They implement the same small internal interface with the CPU oracle so that the
 the drop-ins (index bookkeeping, filters, metric refresh, interpolator dispatch, RNG order, the
 RRT driver, the multi-rank plumbing) can be exercised in the CPU-only container, including against
 the unmodified reference planners.  The product never imports this module."""
+import math
+
 import numpy as np
 
 from oracle import oracle
@@ -205,3 +207,117 @@ class OracleForest(object):
     def _alloc_multi(self):
         if not hasattr(self, "xrand_m"):
             self.xrand_m = [0.0] * (self.T * self.MAX_MULTI * self.dim)
+
+
+class OracleSSTForest(object):
+    """CPU stand-in for backend.CudaSSTForest (csrc/sst.cu): the per-trial sst* iteration restated in Python on top of
+    the oracle's pinned primitives (metric, stepwise CV trajectory end state, sampled control-edge check).  TEST ONLY:
+    it validates the division of labour of sst.SSTStarForest against the unmodified reference where no GPU exists,
+    and it is what the CUDA kernel is compared with on the GPU."""
+
+    def __init__(self, x_dim, u_dim, n_trials, node_cap, witness_cap, dyn, geo, space_spec, device=0):
+        self.X, self.U, self.T = x_dim, u_dim, n_trials
+        self.dyn, self.geo, self.space = dyn, geo, space_spec
+        self.euclid = oracle.MetricSpec.euclidean(x_dim)
+        self.best = [float("inf")] * n_trials
+        self.trials = None
+
+    def _fresh(self, root):
+        return {"x": [list(root)], "parent": [-1], "alive": [True], "active": [True], "c": [0.0], "nch": [0],
+                "wx": [list(root)], "wrep": [0]}
+
+    def reset(self, root):
+        self.root = list(root)
+        self.trials = [self._fresh(root) for _ in range(self.T)]
+        self.best = [float("inf")] * self.T
+
+    @staticmethod
+    def _dist(a, b):
+        s = 0.0
+        for i in range(len(a)):
+            s = s + (a[i] - b[i]) * (a[i] - b[i])
+        return math.sqrt(s)
+
+    def _iterate(self, tr, t, xrand, u, valid, rsel, rwit, goal_c, goal_r, res):
+        X = self.X
+        # pickNode (rrtstarplanner.py:390-410)
+        best_i, best_c = -1, float("inf")
+        for i in range(len(tr["x"])):
+            if tr["alive"][i] and tr["active"][i] and self._dist(tr["x"][i], xrand) <= rsel and tr["c"][i] < best_c:
+                best_i, best_c = i, tr["c"][i]
+        if best_i < 0:
+            bd = float("inf")
+            for i in range(len(tr["x"])):
+                if tr["alive"][i] and tr["active"][i]:
+                    d = self._dist(tr["x"][i], xrand)
+                    if d < bd:
+                        best_i, bd = i, d
+        if best_i < 0:
+            return 1
+        if not valid:
+            return 0
+        xn = tr["x"][best_i]
+        if not oracle.edge_check_control(self.space, self.dyn, self.geo, [xn], [u], res)[0]:
+            return 0
+        xnew = oracle.next_state(self.dyn, [xn], [u])[0].tolist()
+        newcost = tr["c"][best_i] + u[0]
+        # nodeLocallyBest (:345-366)
+        wi, wd = -1, float("inf")
+        for j in range(len(tr["wx"])):
+            d = self._dist(tr["wx"][j], xnew)
+            if d < wd:
+                wi, wd = j, d
+        if wd > rwit:
+            tr["wx"].append(list(xnew))
+            tr["wrep"].append(-1)
+            wi = len(tr["wx"]) - 1
+        else:
+            better = False
+            for j in range(len(tr["wx"])):
+                if self._dist(tr["wx"][j], xnew) <= rwit:
+                    r = tr["wrep"][j]
+                    if r < 0 or newcost < tr["c"][r]:
+                        better = True
+            if not better:
+                return 0
+        n = len(tr["x"])
+        tr["x"].append(xnew)
+        tr["parent"].append(best_i)
+        tr["alive"].append(True)
+        tr["active"].append(True)
+        tr["c"].append(newcost)
+        tr["nch"].append(0)
+        tr["nch"][best_i] += 1
+        # doPruning (:368-388): the NEAREST witness gets the new representative
+        npeer = tr["wrep"][wi]
+        tr["wrep"][wi] = n
+        if npeer >= 0 and npeer != n:
+            tr["active"][npeer] = False
+            while npeer >= 0 and tr["nch"][npeer] == 0 and not tr["active"][npeer]:
+                p = tr["parent"][npeer]
+                tr["alive"][npeer] = False
+                if p >= 0:
+                    tr["nch"][p] -= 1
+                tr["parent"][npeer] = -1
+                npeer = p
+        if goal_r >= 0 and oracle.metric(self.geo, xnew, goal_c) <= goal_r:
+            if newcost < self.best[t]:
+                self.best[t] = newcost
+        return 0
+
+    def step(self, M, xr, uu, valid, sel, wit, restart, goal_c, goal_r, res, restart_now=False, half_sq=None):
+        none = [0] * self.T
+        for t in range(self.T):
+            if restart_now:
+                self.trials[t] = self._fresh(self.root)
+            for m in range(M):
+                if restart[m]:
+                    self.trials[t] = self._fresh(self.root)
+                none[t] += self._iterate(self.trials[t], t, [float(v) for v in xr[t][m]], [float(v) for v in uu[t][m]],
+                                         bool(valid[t][m]), sel[m], wit[m], goal_c, goal_r, res)
+        nodes = [sum(1 for a in tr["alive"] if a) for tr in self.trials]
+        return list(self.best), nodes, none
+
+    def get_trial(self, trial):
+        tr = self.trials[trial]
+        return tr["x"], tr["parent"], tr["alive"]

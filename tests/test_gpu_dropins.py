@@ -358,3 +358,34 @@ def test_device_control_space_nextstate_matches_reference():
                 x = [rng.uniform(-3, 3) for _ in x]
             u = cs.controlSet(x).sample()
             np.testing.assert_allclose(dev.nextState(x, u), cs.nextState(x, u), rtol=1e-5, atol=1e-12)
+
+
+@needs_ref
+def test_sst_star_forest_on_cuda_reproduces_the_reference_per_seed():
+    """BASELINE config 5: 16 seeded sst* trials on DoubleIntegrator in lock step on the GPU (csrc/sst.cu), driven by
+    the caller's own problem objects.  Every trial must reproduce what the UNMODIFIED reference planner produced
+    under its seed (frozen in tests/golden/planners.json: roadmap hash, node count, best path cost after 1000
+    iterations, across the sst* restart at iteration 300), and the oracle-backed stand-in node for node."""
+    refshim.load()
+    from pomp.example_problems import doubleintegrator
+    from pyoptimalmotionplanning_b200.sst import SSTStarForest
+    from tests.fake_backend import OracleSSTForest
+    g = G.load("planners.json")["G3_sststar_forest"]
+    prob = doubleintegrator.doubleIntegratorTest()
+    f = SSTStarForest(prob.controlSpace, prob.start, prob.goal, g["seeds"], prob.objective, selectionRadius=0.3,
+                      witnessRadius=0.3)
+    o = SSTStarForest(prob.controlSpace, prob.start, prob.goal, g["seeds"][:3], prob.objective, selectionRadius=0.3,
+                      witnessRadius=0.3, _backend_factory=OracleSSTForest)
+    done = 0
+    for chunk in (7, 93, 200, 1, 399, 300):           # uneven chunks: the restart falls inside and between launches
+        f.planMore(chunk)
+        o.planMore(chunk)
+        done += chunk
+        for t in range(3):
+            assert f._be.get_trial(t) == tuple(o._be.get_trial(t)), (done, t)
+            assert f.bestPathCost[t] == o.bestPathCost[t]
+    assert done == g["iters"]
+    for t, want in enumerate(g["results"]):
+        V, E = f.getRoadmap(t)
+        got = [hashlib.sha256(repr((V, E)).encode()).hexdigest()[:16], len(V), f.bestPathCost[t]]
+        assert got == want, (g["seeds"][t], got, want)

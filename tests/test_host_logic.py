@@ -409,3 +409,37 @@ def test_edge_checker_dispatch_on_reference_interpolators():
         x = [rng.uniform(0, 6.28), rng.uniform(-10.5, 10.5)]
         e = pp.controlSpace.interpolator(x, pp.controlSpace.controlSet(x).sample())
         assert ref.feasible(e) == mine.feasible(e)
+
+
+@needs_ref
+def test_sst_star_forest_trials_equal_the_reference_planner():
+    """SSTStarForest (lock-step sst* trials, BASELINE config 5) with the oracle-backed stand-in for the device side:
+    every trial reproduces the unmodified reference planner under its seed -- roadmap hash, node count, best cost --
+    across the restart at iteration 300.  (The CUDA kernel is compared with the same stand-in on the GPU.)"""
+    refshim.load()
+    import io
+    import contextlib
+    from pomp.example_problems import doubleintegrator
+    from pyoptimalmotionplanning_b200.sst import SSTStarForest
+    from tests.fake_backend import OracleSSTForest
+    seeds, iters = [7, 8, 3], 700
+    want = []
+    for s in seeds:
+        random.seed(s)
+        prob = doubleintegrator.doubleIntegratorTest()
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = prob.planner("sst*", selectionRadius=0.3, witnessRadius=0.3)
+            p.planMore(iters)
+        V, E = p.getRoadmap()
+        want.append((roadmap_hash(V, E), len(V), p.bestPathCost))
+    prob = doubleintegrator.doubleIntegratorTest()
+    state = random.getstate()
+    f = SSTStarForest(prob.controlSpace, prob.start, prob.goal, seeds, prob.objective, selectionRadius=0.3,
+                      witnessRadius=0.3, _backend_factory=OracleSSTForest)
+    for _ in range(iters // 50):
+        f.planMore(50)
+    assert random.getstate() == state          # the global generator is untouched: every trial has its own stream
+    for t in range(len(seeds)):
+        V, E = f.getRoadmap(t)
+        got = (hashlib.sha256(repr((V, E)).encode()).hexdigest()[:16], len(V), f.bestPathCost[t])
+        assert got == want[t], (t, got, want[t])
