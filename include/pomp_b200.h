@@ -372,6 +372,21 @@ int pomp_forest_extend_multi_h(pomp_forest* f, pomp_space* s, int32_t n_iters, c
                                int32_t* n_done_h, int64_t* parent_h, double* xnew_h, double* edge_len_h,
                                int32_t* added_h);
 
+/* ---------------------------------------------------------------- EST projection-hash density ------------ */
+/* ESTWithProjections (kinodynamicplanner.py:746-868): nodes are hashed per projection basis b (<= 4 coordinates
+   basis_idx[b][i] with scales basis_scale[b][i], rows padded to 4) to the cell key (int(x[k]*v))_k; density(x) =
+   sum_b (#nodes with the key of x in basis b) * basis_weight[b] / n_bases (:834-856; weight = pow(level, 1)).
+   add = onAddNode (:817-832); the node coordinates live on the device, a warp per query counts the matches. */
+typedef struct pomp_est pomp_est;
+int pomp_est_create(int32_t dim, int32_t n_bases, const int32_t* basis_dim_h, const int32_t* basis_idx_h,
+                    const double* basis_scale_h, const double* basis_weight_h, int device, pomp_est** out);
+int pomp_est_destroy(pomp_est* e);
+int pomp_est_reset(pomp_est* e);
+int64_t pomp_est_size(const pomp_est* e);
+int pomp_est_add_h(pomp_est* e, const double* pts_h, int64_t n);
+int pomp_est_density(pomp_est* e, const double* q, int64_t nq, double* out, void* stream);
+int pomp_est_density_h(pomp_est* e, const double* q_h, int64_t nq, double* out_h);
+
 /* ---------------------------------------------------------------- lock-step sst* forest ------------------ */
 /* n_trials independent StableSparseRRT trials (rrtstarplanner.py:203-410 under the restart schedule of
    StableSparseRRTStar :454-471), one block per trial, n_iters planner iterations per call.  The caller supplies, per

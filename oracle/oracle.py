@@ -248,3 +248,23 @@ def set_threads(n):
     L.orc_set_threads.restype = C.c_int
     L.orc_set_threads.argtypes = [C.c_int]
     return int(L.orc_set_threads(int(n)))
+
+
+def est_projection_density(bases, pts, q):
+    """ESTWithProjections.density (kinodynamicplanner.py:834-856) restated with dictionaries, as the reference keeps
+    them (:817-832).  bases: [(indices, scales, weight)]; pts: the nodes; q: query states."""
+    tables = []
+    for idx, sc, w in bases:
+        tab = {}
+        for p_ in pts:
+            key = tuple(int(0.0 + float(p_[k]) * v) for k, v in zip(idx, sc))
+            tab[key] = tab.get(key, 0) + 1
+        tables.append(tab)
+    out = []
+    for x in q:
+        c = 0.0
+        for (idx, sc, w), tab in zip(bases, tables):
+            key = tuple(int(0.0 + float(x[k]) * v) for k, v in zip(idx, sc))
+            c += float(tab.get(key, 0)) * w
+        out.append(c / len(bases))
+    return np.array(out)

@@ -12,12 +12,12 @@ include/pomp_b200.h).  There is no CPU fallback.
 """
 from .descriptors import (MetricSpec, SpaceSpec, DynamicsSpec, metric_from_pomp, space_from_pomp,
                           dynamics_from_pomp)
-from .structures import NearestNeighbors
+from .structures import NearestNeighbors, ProjectionHashDensity
 from .spaces import DeviceSpace, EpsilonEdgeChecker, DeviceControlSpace, BatchedRandomControlSelector
 from .install import install, uninstall, make_checker
 from .sst import SSTStarForest
 from ._abi import PompError, load_library
 
 __all__ = ["MetricSpec", "SpaceSpec", "DynamicsSpec", "metric_from_pomp", "space_from_pomp", "dynamics_from_pomp",
-           "NearestNeighbors", "DeviceSpace", "EpsilonEdgeChecker", "DeviceControlSpace",
+           "NearestNeighbors", "ProjectionHashDensity", "DeviceSpace", "EpsilonEdgeChecker", "DeviceControlSpace",
            "BatchedRandomControlSelector", "SSTStarForest", "install", "uninstall", "make_checker", "PompError", "load_library"]

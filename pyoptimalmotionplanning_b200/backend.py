@@ -420,6 +420,52 @@ class CudaForest(object):
                                                             self.parent_m, self.xnew_m, self.elen_m, self.added_m))
 
 
+class CudaProjectionDensity(object):
+    """ESTWithProjections' hash density on the GPU (pomp_est_* entry points, csrc/est.cu).
+    bases: list of (indices[<=4], scales[<=4], weight)."""
+
+    def __init__(self, dim, bases, device=0):
+        self.lib = _abi.load_library()
+        self.dim = dim
+        nb = len(bases)
+        bd = np.array([len(b[0]) for b in bases], np.int32)
+        bi = np.zeros((nb, 4), np.int32)
+        bs = np.zeros((nb, 4), np.float64)
+        bw = np.array([float(b[2]) for b in bases], np.float64)
+        for j, (idx, sc, _) in enumerate(bases):
+            bi[j, :len(idx)] = idx
+            bs[j, :len(sc)] = sc
+        self._h = C.c_void_p()
+        check(self.lib, self.lib.pomp_est_create(dim, nb, _ptr(bd), _ptr(bi), _ptr(bs), _ptr(bw), device, C.byref(self._h)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self.lib.pomp_est_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(self.lib, self.lib.pomp_est_reset(self._h))
+
+    def size(self):
+        return self.lib.pomp_est_size(self._h)
+
+    def add(self, pts):
+        pts = _f64(pts, self.dim)
+        check(self.lib, self.lib.pomp_est_add_h(self._h, _ptr(pts), len(pts)))
+
+    def density(self, q):
+        q = _f64(q, self.dim)
+        out = np.empty(len(q), np.float64)
+        check(self.lib, self.lib.pomp_est_density_h(self._h, _ptr(q), len(q), _ptr(out)))
+        return out
+
+
 class CudaSSTForest(object):
     """T lock-step sst* trials on one GPU (pomp_sst_* entry points, csrc/sst.cu); the host driver is sst.SSTStarForest."""
 

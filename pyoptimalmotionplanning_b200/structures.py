@@ -288,3 +288,70 @@ class NearestNeighbors(object):
         pts = [self._points[i] for i in keep]
         datas = [self._datas[i] for i in keep]
         self.set(pts, datas)
+
+
+def _density_backend(dim, bases, device):
+    from .backend import CudaProjectionDensity
+    return CudaProjectionDensity(dim, bases, device)
+
+
+class ProjectionHashDensity(object):
+    """The density estimator of ESTWithProjections (kinodynamicplanner.py:746-868) with the node set on the GPU.
+
+    Mirrors the reference's bookkeeping: generateDefaultBases(indices) (:765-815) enumerates all subsets of
+    min(len(indices), 4) coordinates, one single-coordinate basis vector {i: resolution*scale_i} per member, and repeats
+    them `hierarchyLevels` times with the scales multiplied by (1 + level); onAddNode(x) (:817-832) files the node
+    under its integer cell per basis; density(x) (:834-856) averages the (level-weighted) cell populations.  Here the
+    nodes are coordinates on the device and the populations are counted by a kernel (csrc/est.cu); values are
+    bit-identical to the reference's.
+
+    bounds: (bmin, bmax) of the configuration space (controlSpace.configurationSpace().bounds()) or None (scale 1);
+    cost_space: True when the planner runs on a CostControlSpace (the last scale is doubled, :772-773).
+    """
+
+    def __init__(self, dim, bounds=None, resolution=13, hierarchyLevels=2, cost_space=False, indices=None, device=0,
+                 _backend_factory=None):
+        import itertools
+        self.dim = dim
+        self.projectionResolution = resolution
+        self.projectionHierarchyLevels = hierarchyLevels
+        if bounds is not None:
+            scale = [1.0 / (b - a) for (a, b) in zip(bounds[0], bounds[1])]
+            if cost_space:
+                scale[-1] *= 2.0
+        else:
+            scale = [1] * dim
+        indices = list(range(dim)) if indices is None else list(indices)
+        d = min(len(indices), 4)
+        base = []
+        for element in itertools.combinations(indices, d):
+            base.append([(i, resolution * scale[i]) for i in element])
+        bases = list(base)
+        for level in range(1, hierarchyLevels):
+            for b in base:
+                bases.append([(i, v * (1 + level)) for i, v in b])
+        n = len(bases)
+        baselevels = n / hierarchyLevels
+        # density(): blevel = int(index / baselevels) + 1, contribution cnt * pow(blevel, len(basisvector)) with
+        # single-entry basis vectors
+        self.bases = [([i for i, _ in b], [v for _, v in b], float(pow(int(j / baselevels) + 1, 1)))
+                      for j, b in enumerate(bases)]
+        self._be = (_backend_factory or _density_backend)(dim, self.bases, device)
+
+    def reset(self):
+        self._be.reset()
+
+    def __len__(self):
+        return int(self._be.size())
+
+    def onAddNode(self, x):
+        self._be.add([list(x)])
+
+    def add_batch(self, xs):
+        self._be.add(xs)
+
+    def density(self, x):
+        return float(self._be.density([list(x)])[0])
+
+    def density_batch(self, xs):
+        return self._be.density(xs)

@@ -321,3 +321,22 @@ class OracleSSTForest(object):
     def get_trial(self, trial):
         tr = self.trials[trial]
         return tr["x"], tr["parent"], tr["alive"]
+
+
+class OracleProjectionDensity(object):
+    """Stand-in for backend.CudaProjectionDensity.  TEST ONLY."""
+
+    def __init__(self, dim, bases, device=0):
+        self.dim, self.bases, self.pts = dim, bases, []
+
+    def reset(self):
+        self.pts = []
+
+    def size(self):
+        return len(self.pts)
+
+    def add(self, pts):
+        self.pts += [list(p) for p in np.asarray(pts, dtype=np.float64).reshape(-1, self.dim)]
+
+    def density(self, q):
+        return oracle.est_projection_density(self.bases, self.pts, np.asarray(q, dtype=np.float64).reshape(-1, self.dim))

@@ -389,3 +389,55 @@ def test_sst_star_forest_on_cuda_reproduces_the_reference_per_seed():
         V, E = f.getRoadmap(t)
         got = [hashlib.sha256(repr((V, E)).encode()).hexdigest()[:16], len(V), f.bestPathCost[t]]
         assert got == want, (g["seeds"][t], got, want)
+
+
+# ------------------------------------------------------------------ EST projection-hash density
+def test_projection_hash_density_on_cuda_matches_oracle():
+    """pomp_est_* (csrc/est.cu) vs the dictionary restatement of ESTWithProjections.density
+    (kinodynamicplanner.py:817-856): identical floats, including negative coordinates (int() truncates towards zero),
+    cell borders and the cost-space scale."""
+    rng = np.random.default_rng(5)
+    for dim, cost in ((2, False), (4, False), (5, True), (6, False)):
+        lo = -rng.random(dim) - 0.5
+        hi = rng.random(dim) + 0.5
+        dens = P.ProjectionHashDensity(dim, (list(lo), list(hi)), cost_space=cost)
+        pts = lo + rng.random((5000, dim)) * (hi - lo)
+        pts[::17] = np.round(pts[::17] * 13) / 13                      # some nodes exactly on cell borders
+        dens.add_batch(pts[:100])
+        for p in pts[100:140]:
+            dens.onAddNode(list(p))
+        dens.add_batch(pts[140:])
+        assert len(dens) == 5000
+        q = np.concatenate([pts[::50], lo + rng.random((200, dim)) * (hi - lo)])
+        got = dens.density_batch(q)
+        want = oracle.est_projection_density(dens.bases, pts, q)
+        assert (got == want).all()
+        assert dens.density(list(q[3])) == want[3]
+        dens.reset()
+        assert len(dens) == 0 and dens.density(list(q[0])) == 0.0
+
+
+@needs_ref
+def test_projection_hash_density_on_cuda_equals_reference_est():
+    """The unmodified ESTWithProjections next to the device density: same bases, same densities."""
+    refshim.load()
+    from pomp.planners import kinodynamicplanner as KP
+    from pomp.example_problems import doubleintegrator
+    from pomp.spaces.edgechecker import EpsilonEdgeChecker
+    rng = random.Random(3)
+    prob = doubleintegrator.doubleIntegratorTest()
+    cs = prob.controlSpace
+    space = cs.configurationSpace()
+    with contextlib.redirect_stdout(io.StringIO()):
+        est = KP.ESTWithProjections(cs, EpsilonEdgeChecker(space, 0.01))
+        est.setBoundaryConditions(prob.start, None)
+    d = len(prob.start)
+    mine = P.ProjectionHashDensity(d, space.bounds())
+    mine.onAddNode(prob.start)
+    xs = [[rng.uniform(-1.2, 1.2) for _ in range(d)] for _ in range(400)]
+    with contextlib.redirect_stdout(io.StringIO()):
+        for x in xs:
+            est.onAddNode(KP.Node(x))
+    mine.add_batch(xs)
+    for x in xs[:60] + [[rng.uniform(-1.2, 1.2) for _ in range(d)] for _ in range(60)]:
+        assert est.density(x) == mine.density(x)

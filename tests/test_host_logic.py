@@ -443,3 +443,40 @@ def test_sst_star_forest_trials_equal_the_reference_planner():
         V, E = f.getRoadmap(t)
         got = (hashlib.sha256(repr((V, E)).encode()).hexdigest()[:16], len(V), f.bestPathCost[t])
         assert got == want[t], (t, got, want[t])
+
+
+@needs_ref
+def test_projection_hash_density_equals_reference_est():
+    """ESTWithProjections (kinodynamicplanner.py:746-868): the same bases, the same cells, the same densities."""
+    refshim.load()
+    import io
+    import contextlib
+    from pomp.planners import kinodynamicplanner as KP
+    from pomp.example_problems import doubleintegrator, dubins
+    from pomp.spaces.edgechecker import EpsilonEdgeChecker
+    from tests.fake_backend import OracleProjectionDensity
+    rng = random.Random(2)
+    for prob in (doubleintegrator.doubleIntegratorTest(), dubins.dubinsCarTest()):
+        cs = prob.controlSpace
+        space = cs.configurationSpace()
+        with contextlib.redirect_stdout(io.StringIO()):
+            est = KP.ESTWithProjections(cs, EpsilonEdgeChecker(space, 0.01))
+            est.setBoundaryConditions(prob.start, None)
+        try:
+            bounds = space.bounds()
+        except Exception:
+            bounds = None
+        d = len(prob.start)
+        mine = P.ProjectionHashDensity(d, bounds, _backend_factory=OracleProjectionDensity)
+        mine.onAddNode(prob.start)
+        xs = []
+        for _ in range(300):
+            x = [rng.uniform(-1.2, 1.2) for _ in range(d)]
+            xs.append(x)
+            with contextlib.redirect_stdout(io.StringIO()):
+                est.onAddNode(KP.Node(x))
+            mine.onAddNode(x)
+        assert len(est.projectionBases) == len(mine.bases)
+        for _ in range(100):
+            x = rng.choice(xs) if rng.random() < 0.5 else [rng.uniform(-1.2, 1.2) for _ in range(d)]
+            assert est.density(x) == mine.density(x)
