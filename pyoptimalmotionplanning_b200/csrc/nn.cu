@@ -1043,7 +1043,7 @@ static int grid_knn_sort(pomp_nn* h, SortScratch& S, const double* q, int64_t nq
   POMP_TRY(S.qperm.reserve((size_t)nq));
   POMP_TRY(S.ovf.reserve(2 * (size_t)nq + 2));  // two overflow lists; sized HERE: the launchers must not reallocate
                                                  // after query_cell_kernel zeroed the first counter
-  if (fast && h->D == 2) POMP_TRY(S.qsorted.reserve((size_t)nq * h->D));
+  if (fast) POMP_TRY(S.qsorted.reserve((size_t)nq * h->D));
   POMP_TRY(S.scan_tmp.reserve(scan_scratch_elems(nb)));
   int* counts = S.counts.p;
   int* start = S.counts.p + nb + 1;
@@ -1055,11 +1055,11 @@ static int grid_knn_sort(pomp_nn* h, SortScratch& S, const double* q, int64_t nq
   if (nb <= 8192) LAUNCH((scan_small_kernel<int>), 1, 1024, 0, st, counts, (int)nb, start);
   else POMP_TRY(exclusive_scan<int>(counts, nb, start, S.scan_tmp.p, st));
   LAUNCH(query_perm_kernel, blocks, 256, 0, st, S.qcell.p, S.qcell.p + nq, start, q, (long long)nq, h->D, S.qperm.p,
-         (fast && h->D == 2) ? S.qsorted.p : (double*)nullptr);
+         fast ? S.qsorted.p : (double*)nullptr);
   CHECK_LAUNCH();
   info->qperm = S.qperm.p;
   info->qstart = start;
-  if (fast && h->D == 2) info->qsorted = S.qsorted.p;
+  if (fast) info->qsorted = S.qsorted.p;
   info->shift = shift;
   info->nbx = nbx;
   return POMP_OK;
@@ -1076,6 +1076,7 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
   (void)qstart;
   (void)shift;
   (void)nbx;
+  if (fast && warp_knn_eligible(h, k)) return launch_grid_knn_warp(h, q, qsorted, nq, qperm, k, idx, dist, cnt, st);
   if (fast) {
     switch (h->D) {
       case 2: {
@@ -1605,6 +1606,8 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "max_tail") h->max_tail = value;
   else if (s == "block_search") h->block_search = value;
   else if (s == "block_need") h->block_need = value;
+  else if (s == "warp_search") h->warp_search = value;
+  else if (s == "warp_need") h->warp_need = value;
   else if (s == "strip_search") h->strip_search = value;
   else if (s == "strip_spin_ns") h->strip_spin_ns = value;
   else if (s == "strip_probe") h->strip_probe = value;

@@ -62,6 +62,8 @@ struct pomp_nn {
   double bf_tiled = 1;      // brute-force regime, Euclidean k = 1 batches: shared-memory tiled kernel
   double se2_fast = 1;      // SE(2) product metric: compile-time kernel (grid_se2.cuh) instead of the generic one
   double block_need = 0;    // k = 1: expected points in the certified ball that selects the block radius (0 = default)
+  double warp_search = 1;   // Euclidean k-NN: warp-per-query shell kernel (grid_warp.cuh); 0 off, 1 where it wins, 2 always
+  double warp_need = 0;     // expected points inside its first shell (0 = k + 1.5 sqrt(k) + 1; 3 for k = 1)
   double block_search = 1;  // 2-D Euclidean: fixed block of cells + certificate (0: pruned traversal; 2: also in 3-D)
   // scratch for queries
   DevBuf<double> q_dev;
@@ -165,6 +167,10 @@ int launch_grid_knn_flat2d(pomp_nn* h, const double* q, const double* qsorted, i
 // overflow lists of a first-stage 2-D search: flat kernel with the next larger block, then the pruned traversal
 int launch_overflow_2d(pomp_nn* h, const double* q, int64_t nq, int k, int* l1, int* c1, int* l2, int* c2, int64_t* idx,
                        double* dist, int32_t* cnt, cudaStream_t st);
+// nn_warp.cu: warp-per-query shell kernel (grid_warp.cuh)
+bool warp_knn_eligible(const pomp_nn* h, int k);
+int launch_grid_knn_warp(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm, int k, int64_t* idx, double* dist,
+                         int32_t* cnt, cudaStream_t st);
 // strip2d.cu: streaming nearest-neighbour search over the strip index
 bool strip_eligible(const pomp_nn* h, int64_t nq, int k);
 int strip_nearest(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,

@@ -1,0 +1,73 @@
+// nn_warp.cu -- launcher of the warp-per-query k-NN kernel (grid_warp.cuh).
+#include "common.cuh"
+#include "grid.cuh"
+#include "grid_warp.cuh"
+#include "nn_handle.cuh"
+
+using namespace pomp;
+
+// volume of the unit ball in D dimensions
+static double unit_ball(int D) {
+  switch (D) {
+    case 1: return 2.0;
+    case 2: return 3.141592653589793;
+    case 3: return 4.1887902047863905;
+    case 4: return 4.934802200544679;
+    case 5: return 5.263789013914325;
+    default: return 5.167712780049970;
+  }
+}
+
+bool pomp::warp_knn_eligible(const pomp_nn* h, int k) {
+  if (h->warp_search == 0 || k > 32) return false;
+  if (!(h->D == 2 || h->D == 3 || h->D == 4 || h->D == 6)) return false;
+  if (h->grid.n_cells >= 0x7fffffffLL - 64) return false;
+  if (h->warp_search >= 2) return true;
+  // measured on B200 (2^20 queries vs 2^24 points, thread-per-query -> warp-per-query): 3-D k = 16 4.6 -> 2.45 ms,
+  // 4-D k = 16 7.7 -> 4.0 ms, 6-D k = 16 29 -> 19-21 ms, 6-D k = 1 9.3 -> 7.2 ms; the thread kernels keep 2-D
+  // (k = 16: 1.20 vs 1.53 ms) and k = 1 in 3-D / 4-D (0.52 vs 1.4, 1.18 vs 2.0 ms)
+  if (h->D == 2) return false;
+  if (h->D == 6) return true;
+  return k >= 8;
+}
+
+int pomp::launch_grid_knn_warp(pomp_nn* h, const double* q, const double* qsorted, int64_t nq, const int* qperm, int k, int64_t* idx,
+                               double* dist, int32_t* cnt, cudaStream_t st) {
+  const GridDev& g = h->grid;
+  const int D = h->D;
+  // first shell: the radius expected to hold `need` points at the mean density of the bounding box
+  double vol = 1.0, diag = 0.0, hmin = 1e300;
+  for (int a = 0; a < D; a++) {
+    const double ext = g.hi[a] - g.lo[a];
+    vol *= ext > 0.0 ? ext : 1.0;
+    diag += ext > 0.0 ? ext : 0.0;
+    if (g.h[a] > 0.0) hmin = std::min(hmin, g.h[a]);
+  }
+  if (!(hmin < 1e300)) hmin = 1.0;
+  const double need = h->warp_need > 0 ? h->warp_need : (k == 1 ? 3.0 : (double)k + 1.5 * sqrt((double)k) + 1.0);
+  double r0 = pow(need * vol / (std::max(1, g.n_indexed) * unit_ball(D)), 1.0 / D);
+  if (!(r0 > 0.0) || !std::isfinite(r0)) r0 = hmin;
+  r0 = std::max(r0, 1e-3 * hmin);
+  const double rmax = 4.0 * diag + 4.0 * r0;
+  const int blocks = (int)((nq + WQ_WARPS - 1) / WQ_WARPS);
+  const uint8_t* skip = h->skip_ptr();
+#define WK(DD, K1)                                                                                                  \
+  LAUNCH((grid_knn_warp_kernel<DD, K1>), blocks, WQ_WARPS * 32, 0, st, g, h->d_pts, (long long)h->n_dev, skip, q, \
+         qsorted, (long long)nq, qperm, k, r0, rmax, idx, dist, cnt)
+  prof_begin(h, st);
+  if (k == 1) {
+    if (D == 2) WK(2, true);
+    else if (D == 3) WK(3, true);
+    else if (D == 4) WK(4, true);
+    else WK(6, true);
+  } else {
+    if (D == 2) WK(2, false);
+    else if (D == 3) WK(3, false);
+    else if (D == 4) WK(4, false);
+    else WK(6, false);
+  }
+#undef WK
+  prof_end(h, st);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}

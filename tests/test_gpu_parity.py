@@ -803,3 +803,102 @@ def test_spatial_shard_kernels_match_numpy_ops():
     ooff, ohits = oracle.nn_neighbors(m, big, bq[:2000], 0.004, True)
     assert (off.cpu().numpy() == ooff).all() and (hits.cpu().numpy() == ohits).all()
     dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ warp-per-query shell kernel (grid_warp.cuh)
+def _lexsort_knn(pts, q, k, mask=None):
+    """NumPy brute force with the library's tie rule: the k smallest (distance, insertion index) keys; distances
+    summed in coordinate order like vectorops.distance (vectorops.py:94-102)."""
+    s = np.zeros((len(q), len(pts)))
+    for j in range(pts.shape[1]):
+        t = pts[None, :, j] - q[:, None, j]
+        s = s + t * t
+    dd = np.sqrt(s)
+    if mask is not None:
+        dd = np.where(mask[None, :] != 0, np.inf, dd)
+    order = np.lexsort((np.broadcast_to(np.arange(len(pts)), dd.shape), dd), axis=1)[:, :k]
+    od = np.take_along_axis(dd, order, axis=1)
+    oi = np.where(np.isfinite(od), order, -1)
+    return oi, od
+
+
+@pytest.mark.parametrize("D", [2, 3, 4, 6])
+@pytest.mark.parametrize("k", [1, 5, 16, 32])
+def test_warp_shell_kernel_matches_oracle(D, k):
+    """warp_search = 2 forces the warp-per-query kernel for every Euclidean (D, k): uniform cloud, queries outside
+    the bounding box, sorted (large) and unsorted (small) batches, several first-shell radii (too small -> radius
+    doubling and second shells; too large -> one fat shell)."""
+    rng = np.random.default_rng(500 + 10 * D + k)
+    n = 150000
+    pts = rng.random((n, D))
+    q = np.concatenate([rng.random((1900, D)), rng.random((100, D)) * 1.6 - 0.3])
+    m = MetricSpec.euclidean(D)
+    oi, od, oc = oracle.nn_knearest(m, pts, q, k)
+    for need in (0, 0.05, 40 * k):
+        nn = _nn(m, pts, grid=True)
+        nn.set_param("warp_search", 2)
+        nn.set_param("warp_need", need)
+        nn.set_param("sort_min_queries", 1000)
+        idx, dist, cnt = nn.knearest(q, k)
+        assert (cnt == oc).all(), need
+        assert (idx == oi).all(), need
+        assert (dist == od).all(), need
+        idx, dist, cnt = nn.knearest(q[:300], k)          # below the sort threshold: qperm = NULL
+        assert (idx == oi[:300]).all() and (dist == od[:300]).all()
+    if k == 1:
+        i1, d1 = nn.nearest(q)
+        assert (i1 == oi[:, 0]).all() and (d1 == od[:, 0]).all()
+
+
+@pytest.mark.parametrize("D", [2, 3, 6])
+def test_warp_shell_kernel_masks_tail_ties_and_clusters(D):
+    rng = np.random.default_rng(77 + D)
+    m = MetricSpec.euclidean(D)
+    # (1) tombstones + reject mask + unindexed tail; more than half of the points masked in one corner, so lists
+    # stay short after the first shells
+    pts = rng.random((40000, D))
+    q = rng.random((600, D))
+    nn = _nn(m, pts[:38000], grid=True)
+    nn.set_param("warp_search", 2)
+    nn.build_index()
+    nn.add(pts[38000:])
+    mask = np.zeros(40000, np.uint8)
+    mask[(pts[:, 0] < 0.6) & (pts[:, 1] < 0.7)] = 1
+    mask[rng.choice(40000, 3000, replace=False)] = 1
+    nn.set_mask(mask)
+    for k in (1, 7, 32):
+        idx, dist, cnt = nn.knearest(q, k)
+        oi, od, oc = oracle.nn_knearest(m, pts, q, k, mask)
+        assert (idx == oi).all() and (dist == od).all() and (cnt == oc).all(), k
+    # (2) lattice with duplicates: exact ties everywhere, the lowest insertion indices win
+    side = {2: 40, 3: 12, 6: 3}[D]
+    g = np.stack(np.meshgrid(*([np.arange(side) / side] * D), indexing="ij"), -1).reshape(-1, D)
+    lat = np.concatenate([g, g[::3], g[::5]])
+    ql = np.concatenate([g[::7] + 0.5 / side * 0.5, g[::11], rng.random((50, D))])
+    nn = _nn(m, lat, grid=True)
+    nn.set_param("warp_search", 2)
+    for k in (1, 6, 20):
+        oi, od = _lexsort_knn(lat, ql, k)
+        idx, dist, cnt = nn.knearest(ql, k)
+        assert (dist == od).all(), k
+        assert (idx == oi).all(), k
+    # (3) clustered cloud (the global density is useless there), fewer points than k, non-finite queries
+    centres = rng.random((20, D))
+    clu = centres[rng.integers(0, 20, 60000)] + rng.normal(0, 0.002, (60000, D))
+    qc = np.concatenate([clu[::200] + rng.normal(0, 0.001, (300, D)), rng.random((100, D))])
+    nn = _nn(m, clu, grid=True)
+    nn.set_param("warp_search", 2)
+    for k in (1, 16):
+        oi, od, oc = oracle.nn_knearest(m, clu, qc, k)
+        idx, dist, cnt = nn.knearest(qc, k)
+        assert (idx == oi).all() and (dist == od).all(), k
+    few = rng.random((20, D))
+    nn = _nn(m, few, grid=True)
+    nn.set_param("warp_search", 2)
+    qf = rng.random((70, D))
+    qf[3, 0] = np.nan
+    qf[5, D - 1] = np.inf
+    idx, dist, cnt = nn.knearest(qf, 32)
+    oi, od, oc = oracle.nn_knearest(m, few, qf, 32)
+    assert (idx == oi).all() and (cnt == oc).all()
+    assert cnt[3] == 0 and cnt[5] == 0 and (cnt[[0, 1, 2]] == 20).all()
