@@ -22,13 +22,16 @@ for D in Ds:
         dst = torch.empty((nq, K), dtype=torch.float64, device="cuda")
         ref = None
         variants = [("thread", 0, 0, 0)]
-        for ppc in ((0, 3, 6) if D <= 3 else (0, 8, 16)):
-            for need in (0,) + ((2, 5) if K == 1 else (K, 1.6 * K)):
-                variants.append(("warp", ppc, need, 2))
+        for lanes in (8, 16, 32):
+            for ppc in (0,) + ((8,) if D >= 4 else ()):
+                for need in (0,) + ((5,) if K == 1 else (1.6 * K,)):
+                    variants.append(("warp%d" % lanes, ppc, need, 2))
         for name, ppc, need, ws in variants:
             nn = CudaNN(MetricSpec.euclidean(D), 0)
             nn.set_param("warp_search", ws)
             nn.set_param("warp_need", need)
+            if name.startswith("warp"):
+                nn.set_param("warp_lanes", int(name[4:]))
             if ppc:
                 nn.set_param("points_per_cell", ppc)
             nn.set_device(pts.data_ptr(), n, st)

@@ -1608,6 +1608,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "block_need") h->block_need = value;
   else if (s == "warp_search") h->warp_search = value;
   else if (s == "warp_need") h->warp_need = value;
+  else if (s == "warp_lanes") h->warp_lanes = value;
   else if (s == "strip_search") h->strip_search = value;
   else if (s == "strip_spin_ns") h->strip_spin_ns = value;
   else if (s == "strip_probe") h->strip_probe = value;

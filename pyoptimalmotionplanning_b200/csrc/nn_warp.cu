@@ -49,23 +49,35 @@ int pomp::launch_grid_knn_warp(pomp_nn* h, const double* q, const double* qsorte
   if (!(r0 > 0.0) || !std::isfinite(r0)) r0 = hmin;
   r0 = std::max(r0, 1e-3 * hmin);
   const double rmax = 4.0 * diag + 4.0 * r0;
-  const int blocks = (int)((nq + WQ_WARPS - 1) / WQ_WARPS);
   const uint8_t* skip = h->skip_ptr();
-#define WK(DD, K1)                                                                                                  \
-  LAUNCH((grid_knn_warp_kernel<DD, K1>), blocks, WQ_WARPS * 32, 0, st, g, h->d_pts, (long long)h->n_dev, skip, q, \
-         qsorted, (long long)nq, qperm, k, r0, rmax, idx, dist, cnt)
+  // lanes per query.  Measured (2^20 queries vs 2^24 points, W = 8 / 16 / 32): k = 1: 3-D 0.85 / 1.07 / 1.47 ms, 4-D
+  // 1.57 / 1.69 / 1.99 ms, 6-D 9.7 / 8.5 / 7.2 ms; k = 16 (no bulk merge below W = 32): 3-D 6.5 / 4.6 / 2.4 ms,
+  // 6-D 45 / 29 / 20 ms
+  int W = (int)h->warp_lanes;
+  if (!(W == 8 || W == 16 || W == 32)) W = 32;
+#define WK(DD, K1, WW)                                                                                              \
+  LAUNCH((grid_knn_warp_kernel<DD, K1, WW>), (int)((nq + (WQ_WARPS * 32 / WW) - 1) / (WQ_WARPS * 32 / WW)),        \
+         WQ_WARPS * 32, 0, st, g, h->d_pts, (long long)h->n_dev, skip, q, qsorted, (long long)nq, qperm, k, r0,     \
+         rmax, idx, dist, cnt)
+#define WKW(DD, K1)            \
+  do {                         \
+    if (W == 8) WK(DD, K1, 8); \
+    else if (W == 16) WK(DD, K1, 16); \
+    else WK(DD, K1, 32);       \
+  } while (0)
   prof_begin(h, st);
   if (k == 1) {
-    if (D == 2) WK(2, true);
-    else if (D == 3) WK(3, true);
-    else if (D == 4) WK(4, true);
-    else WK(6, true);
+    if (D == 2) WKW(2, true);
+    else if (D == 3) WKW(3, true);
+    else if (D == 4) WKW(4, true);
+    else WKW(6, true);
   } else {
-    if (D == 2) WK(2, false);
-    else if (D == 3) WK(3, false);
-    else if (D == 4) WK(4, false);
-    else WK(6, false);
+    if (D == 2) WKW(2, false);
+    else if (D == 3) WKW(3, false);
+    else if (D == 4) WKW(4, false);
+    else WKW(6, false);
   }
+#undef WKW
 #undef WK
   prof_end(h, st);
   CHECK_LAUNCH();

@@ -822,9 +822,10 @@ def _lexsort_knn(pts, q, k, mask=None):
     return oi, od
 
 
+@pytest.mark.parametrize("lanes", [8, 16, 32])
 @pytest.mark.parametrize("D", [2, 3, 4, 6])
 @pytest.mark.parametrize("k", [1, 5, 16, 32])
-def test_warp_shell_kernel_matches_oracle(D, k):
+def test_warp_shell_kernel_matches_oracle(D, k, lanes):
     """warp_search = 2 forces the warp-per-query kernel for every Euclidean (D, k): uniform cloud, queries outside
     the bounding box, sorted (large) and unsorted (small) batches, several first-shell radii (too small -> radius
     doubling and second shells; too large -> one fat shell)."""
@@ -837,6 +838,7 @@ def test_warp_shell_kernel_matches_oracle(D, k):
     for need in (0, 0.05, 40 * k):
         nn = _nn(m, pts, grid=True)
         nn.set_param("warp_search", 2)
+        nn.set_param("warp_lanes", lanes)
         nn.set_param("warp_need", need)
         nn.set_param("sort_min_queries", 1000)
         idx, dist, cnt = nn.knearest(q, k)
@@ -850,8 +852,9 @@ def test_warp_shell_kernel_matches_oracle(D, k):
         assert (i1 == oi[:, 0]).all() and (d1 == od[:, 0]).all()
 
 
+@pytest.mark.parametrize("lanes", [8, 32])
 @pytest.mark.parametrize("D", [2, 3, 6])
-def test_warp_shell_kernel_masks_tail_ties_and_clusters(D):
+def test_warp_shell_kernel_masks_tail_ties_and_clusters(D, lanes):
     rng = np.random.default_rng(77 + D)
     m = MetricSpec.euclidean(D)
     # (1) tombstones + reject mask + unindexed tail; more than half of the points masked in one corner, so lists
@@ -860,6 +863,7 @@ def test_warp_shell_kernel_masks_tail_ties_and_clusters(D):
     q = rng.random((600, D))
     nn = _nn(m, pts[:38000], grid=True)
     nn.set_param("warp_search", 2)
+    nn.set_param("warp_lanes", lanes)
     nn.build_index()
     nn.add(pts[38000:])
     mask = np.zeros(40000, np.uint8)
@@ -877,6 +881,7 @@ def test_warp_shell_kernel_masks_tail_ties_and_clusters(D):
     ql = np.concatenate([g[::7] + 0.5 / side * 0.5, g[::11], rng.random((50, D))])
     nn = _nn(m, lat, grid=True)
     nn.set_param("warp_search", 2)
+    nn.set_param("warp_lanes", lanes)
     for k in (1, 6, 20):
         oi, od = _lexsort_knn(lat, ql, k)
         idx, dist, cnt = nn.knearest(ql, k)
@@ -888,6 +893,7 @@ def test_warp_shell_kernel_masks_tail_ties_and_clusters(D):
     qc = np.concatenate([clu[::200] + rng.normal(0, 0.001, (300, D)), rng.random((100, D))])
     nn = _nn(m, clu, grid=True)
     nn.set_param("warp_search", 2)
+    nn.set_param("warp_lanes", lanes)
     for k in (1, 16):
         oi, od, oc = oracle.nn_knearest(m, clu, qc, k)
         idx, dist, cnt = nn.knearest(qc, k)
@@ -895,6 +901,7 @@ def test_warp_shell_kernel_masks_tail_ties_and_clusters(D):
     few = rng.random((20, D))
     nn = _nn(m, few, grid=True)
     nn.set_param("warp_search", 2)
+    nn.set_param("warp_lanes", lanes)
     qf = rng.random((70, D))
     qf[3, 0] = np.nan
     qf[5, D - 1] = np.inf
