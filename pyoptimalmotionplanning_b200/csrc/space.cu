@@ -69,8 +69,68 @@ __device__ __forceinline__ int warp_incl_scan_i(int v) {
   return v;
 }
 
+// EpsilonEdgeChecker's result is a pure conjunction over the endpoints and the k interior samples, so they may be
+// evaluated in any order -- used three times here:
+//   * the samples are laid out SAMPLE-MAJOR over the edges that are still alive: a round takes the next S samples of
+//     each of the A alive edges (A * S <= 64 items, two per lane), then drops the edges that failed or are complete
+//     (edge-major order evaluated all k samples of an edge whose second sample already hits an obstacle: at res 0.001,
+//     150 samples per edge, 23 rounds per warp instead of 2);
+//   * a round only CLASSIFIES its points with the fine occupancy map (one load): empty cells pass, full cells fail;
+//   * the points of partially covered cells are parked in a per-warp queue and tested against their buckets 64 at a
+//     time (two dependent loads, all lanes busy, two points per lane), while their edges go on sampling.
+constexpr int EQ_CAP = 160;  // queue entries per warp; popped when fewer than 64 slots (one round's worth) are free
+struct EdgeQueue {
+  double x[EQ_CAP], y[EQ_CAP];
+  int owner[EQ_CAP];
+  unsigned char rank2lane[32];
+};
+
+__device__ __forceinline__ void edge_queue_push(EdgeQueue& Q, int& qn, bool push, double px, double py, int owner) {
+  const unsigned m = __ballot_sync(0xffffffffu, push);
+  if (push) {
+    const int at = qn + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+    Q.x[at] = px;
+    Q.y[at] = py;
+    Q.owner[at] = owner;
+  }
+  qn += __popc(m);
+}
+
+// tests the top min(qn, 64) queued points against their buckets, two per lane with their range loads in flight
+// together; points of edges that failed meanwhile are skipped
+__device__ __forceinline__ void edge_queue_pop64(const SpaceDev& s, EdgeQueue& Q, int& qn, unsigned* failbits) {
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  const int take = min(qn, 64);
+  const unsigned fb = *(volatile unsigned*)failbits;
+  bool act[2];
+  double px[2], py[2];
+  int ow[2], b[2], e[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int t = h * 32 + lane;
+    act[h] = t < take;
+    ow[h] = 0;
+    px[h] = py[h] = 0.0;
+    b[h] = e[h] = 0;
+    if (act[h]) {
+      const int at = qn - take + t;
+      ow[h] = Q.owner[at];
+      px[h] = Q.x[at];
+      py[h] = Q.y[at];
+      act[h] = !((fb >> ow[h]) & 1u);
+      if (act[h]) bucket_range(s, px[h], py[h], b[h], e[h]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+    if (act[h] && bucket_scan(s, b[h], e[h], px[h], py[h])) atomicOr(failbits, 1u << ow[h]);
+  qn -= take;
+  __syncwarp();
+}
+
 __device__ __forceinline__ bool edge_batch_warp2d(const SpaceDev& s, double2 a, double2 b, bool valid, double res,
-                                                  unsigned* failbits /* one word per warp, shared */) {
+                                                  unsigned* failbits /* one word per warp, shared */, EdgeQueue& Q) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double pa[2] = {a.x, a.y}, pb[2] = {b.x, b.y};
@@ -80,39 +140,116 @@ __device__ __forceinline__ bool edge_batch_warp2d(const SpaceDev& s, double2 a, 
   l = l + t1 * t1;
   l = sqrt(l);
   long long k = valid ? edge_samples(s, l, res) : 0;
-  bool alive = valid && k >= 0 && feasible_pt(s, pa) && feasible_pt(s, pb);
   const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
-  bool big = k > 4096;  // pathological resolution: this lane walks its own edge afterwards
-  int cnt = (alive && !big) ? (int)k : 0;
-  int incl = warp_incl_scan_i(cnt);
-  int excl = incl - cnt;
-  int total = __shfl_sync(FULL, incl, 31);
+  const bool big = k > 4096;  // pathological resolution: this lane walks its own edge afterwards
+  // without an obstacle grid (a handful of obstacles) or with NaN coordinates the plain loop decides at once
+  const bool mapped = s.use_grid != 0;
+  // BoxSet.contains on both coordinates (sets.py:177-182); NaN passes, as in Python
+  auto inb = [&](double x0, double x1) { return !(x0 < s.lo[0] || x0 > s.hi[0] || x1 < s.lo[1] || x1 > s.hi[1]); };
+  bool alive = valid && k >= 0 && inb(pa[0], pa[1]) && inb(pb[0], pb[1]);
+  if (__all_sync(FULL, !valid || (k >= 0 && k <= 2))) {
+    // a warp of short edges (roadmap edges to near neighbours: one or two samples each): the queue machinery costs
+    // more than it saves, every lane walks its own edge
+    bool okv = alive;
+    if (okv) okv = !hits_obstacle(s, s.od0 ? pa[1] : pa[0], s.od1 ? pa[1] : pa[0]);
+    if (okv) okv = !hits_obstacle(s, s.od0 ? pb[1] : pb[0], s.od1 ? pb[1] : pb[0]);
+    for (int i = 0; okv && i < (int)k; i++) {
+      const double u = (double)(i + 1) / (double)(k + 2);
+      const double x0 = pa[0] + u * dx, x1 = pa[1] + u * dy;
+      okv = inb(x0, x1) && !hits_obstacle(s, s.od0 ? x1 : x0, s.od1 ? x1 : x0);
+    }
+    return okv;
+  }
   if (lane == 0) *failbits = 0u;
   __syncwarp();
-  for (int base = 0; base < total; base += 32) {
-    int j = base + lane;
-    int owner = 0;
+  int qn = 0;
+  unsigned char* rank2lane = Q.rank2lane;
+  // ---- endpoints: two more members of the conjunction
+  {
+    bool push[2] = {false, false};
+    double epx[2], epy[2];
 #pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-      int cand = owner + step;
-      int ce = __shfl_sync(FULL, excl, cand & 31);
-      if (cand < 32 && ce <= j) owner = cand;
+    for (int h = 0; h < 2; h++) {
+      const double e0 = h ? pb[0] : pa[0], e1 = h ? pb[1] : pa[1];
+      const double px = s.od0 ? e1 : e0, py = s.od1 ? e1 : e0;
+      epx[h] = px;
+      epy[h] = py;
+      if (alive) {
+        if (!mapped || isnan(px) || isnan(py)) {
+          if (hits_obstacle(s, px, py)) alive = false;
+        } else {
+          const int cls = obs_class(s, px, py);
+          if (cls == OBS_FULL) alive = false;
+          push[h] = cls == OBS_PART;
+        }
+      }
     }
-    int oe = __shfl_sync(FULL, excl, owner);
-    int ok_ = __shfl_sync(FULL, cnt, owner);
-    double ax = __shfl_sync(FULL, pa[0], owner), ay = __shfl_sync(FULL, pa[1], owner);
-    double ddx = __shfl_sync(FULL, dx, owner), ddy = __shfl_sync(FULL, dy, owner);
-    unsigned fb = *(volatile unsigned*)failbits;
-    bool act = j < total && !((fb >> owner) & 1u);
-    if (act) {
-      int i = j - oe;
-      double u = (double)(i + 1) / (double)(ok_ + 2);
-      double x[2] = {ax + u * ddx, ay + u * ddy};
-      if (!feasible_pt(s, x)) atomicOr(failbits, 1u << owner);
-    }
-    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+      edge_queue_push(Q, qn, push[h] && alive, epx[h], epy[h], lane);
   }
-  bool fail = ((*(volatile unsigned*)failbits) >> lane) & 1u;
+  const int cnt = (alive && !big) ? (int)k : 0;
+  unsigned live = __ballot_sync(FULL, cnt > 0) & ~(*(volatile unsigned*)failbits);  // edges with samples left
+  int sbase = 0;                                                                    // samples of every live edge done
+  while (live) {
+    const int A = __popc(live);
+    const int S = 64 / A;  // >= 2
+    const float invA = __frcp_rn((float)A);
+    // lane of the r-th live edge (a table instead of __fns, which is a software loop)
+    if ((live >> lane) & 1u) rank2lane[__popc(live & ((1u << lane) - 1u))] = (unsigned char)lane;
+    __syncwarp();
+    bool push[2];
+    double qx[2], qy[2];
+    int own[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int j = h * 32 + lane;
+      int sj = (int)(__int2float_rz(j) * invA);  // j / A, off by at most one
+      int r = j - sj * A;
+      if (r < 0) {
+        r += A;
+        sj--;
+      } else if (r >= A) {
+        r -= A;
+        sj++;
+      }
+      own[h] = rank2lane[r];
+      const int smp = sbase + sj;
+      const int ok_ = __shfl_sync(FULL, cnt, own[h]);
+      const double ax = __shfl_sync(FULL, pa[0], own[h]), ay = __shfl_sync(FULL, pa[1], own[h]);
+      const double ddx = __shfl_sync(FULL, dx, own[h]), ddy = __shfl_sync(FULL, dy, own[h]);
+      push[h] = false;
+      qx[h] = qy[h] = 0.0;
+      if (j < A * S && smp < ok_) {
+        const double u = (double)(smp + 1) / (double)(ok_ + 2);
+        const double x0 = ax + u * ddx, x1 = ay + u * ddy;
+        const double px = s.od0 ? x1 : x0, py = s.od1 ? x1 : x0;
+        bool hit;
+        if (!inb(x0, x1)) {
+          hit = true;
+        } else if (!mapped || isnan(px) || isnan(py)) {
+          hit = hits_obstacle(s, px, py);
+        } else {
+          const int cls = obs_class(s, px, py);
+          hit = cls == OBS_FULL;
+          push[h] = cls == OBS_PART;
+          qx[h] = px;
+          qy[h] = py;
+        }
+        if (hit) atomicOr(failbits, 1u << own[h]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) edge_queue_push(Q, qn, push[h], qx[h], qy[h], own[h]);
+    if (qn > EQ_CAP - 64) edge_queue_pop64(s, Q, qn, failbits);
+    __syncwarp();
+    sbase += S;
+    live &= ~(*(volatile unsigned*)failbits);
+    live &= __ballot_sync(FULL, cnt > sbase);
+  }
+  while (qn > 0) edge_queue_pop64(s, Q, qn, failbits);
+  __syncwarp();
+  const bool fail = ((*(volatile unsigned*)failbits) >> lane) & 1u;
   __syncwarp();
   bool okv = alive && !fail;
   if (okv && big) {
@@ -133,6 +270,7 @@ __global__ void __launch_bounds__(128)
 edge_check_warp2d_kernel(SpaceDev s, const double* __restrict__ a, const double* __restrict__ b, long long n,
                          double res, uint8_t* __restrict__ ok) {
   __shared__ unsigned failbits[4];
+  __shared__ EdgeQueue queues[4];
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = i < n;
   double2 va = make_double2(0, 0), vb = make_double2(0, 0);
@@ -140,7 +278,7 @@ edge_check_warp2d_kernel(SpaceDev s, const double* __restrict__ a, const double*
     va = __ldg(reinterpret_cast<const double2*>(a) + i);
     vb = __ldg(reinterpret_cast<const double2*>(b) + i);
   }
-  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5]);
+  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5], queues[threadIdx.x >> 5]);
   if (valid) ok[i] = r ? 1 : 0;
 }
 
@@ -148,6 +286,7 @@ __global__ void __launch_bounds__(128)
 edge_check_indexed_warp2d_kernel(SpaceDev s, const double* __restrict__ nodes, const int* __restrict__ ij,
                                  long long n, double res, uint8_t* __restrict__ ok) {
   __shared__ unsigned failbits[4];
+  __shared__ EdgeQueue queues[4];
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = e < n;
   double2 va = make_double2(0, 0), vb = make_double2(0, 0);
@@ -156,7 +295,7 @@ edge_check_indexed_warp2d_kernel(SpaceDev s, const double* __restrict__ nodes, c
     va = __ldg(reinterpret_cast<const double2*>(nodes) + pr.x);
     vb = __ldg(reinterpret_cast<const double2*>(nodes) + pr.y);
   }
-  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5]);
+  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5], queues[threadIdx.x >> 5]);
   if (valid) ok[e] = r ? 1 : 0;
 }
 
@@ -419,6 +558,49 @@ static int build_obstacle_grid(pomp_space* sp, const pomp_space_desc* d, cudaStr
   }
   CUDA_TRY(cudaMalloc((void**)&sp->d_cell_geom, sizeof(double) * geom.size()));
   CUDA_TRY(cudaMemcpyAsync(sp->d_cell_geom, geom.data(), sizeof(double) * geom.size(), cudaMemcpyHostToDevice, st));
+  // fine occupancy map (space.cuh).  PART: every cell between the cells of an obstacle's corners (obs_cell is monotone,
+  // so no point of the obstacle maps outside that range).  FULL: the cells STRICTLY between the corner cells of a box
+  // on both axes -- every x of such a cell satisfies x0 < x < x1 (x <= x0 would put it into a cell <= cell(x0)),
+  // likewise y, so the box test returns true for every point of the cell.
+  s.fine = nullptr;
+  s.fnx = s.fny = 0;
+  s.finv0 = s.finv1 = 0.0;
+  {
+    const char* ff = getenv("POMP_OBS_FINE_FACTOR");  // fine cells per obstacle (0: no map)
+    const double ffac = ff ? atof(ff) : 256.0;
+    int fres = (int)ceil(sqrt(ffac * no));
+    fres = std::min(fres, 8192);
+    if (ffac > 0.0 && fres >= 16) {
+      fres = (fres + 15) / 16 * 16;
+      const double fi0 = (double)fres / e0, fi1 = (double)fres / e1;
+      std::vector<unsigned> fine(((size_t)fres * fres + 15) / 16, 0u);
+      auto put = [&](int cx, int cy, unsigned code) {
+        const size_t c = (size_t)cy * fres + cx;
+        unsigned& w = fine[c >> 4];
+        const int sh = (int)(c & 15) * 2;
+        const unsigned cur = (w >> sh) & 3u;
+        if (cur == (unsigned)OBS_FULL) return;  // FULL wins
+        w = (w & ~(3u << sh)) | (code << sh);
+      };
+      for (int o = 0; o < no; o++) {
+        if (!(ox0[o] <= ox1[o]) || !(oy0[o] <= oy1[o])) continue;
+        const int cx0 = obs_cell(ox0[o], glo0, fi0, fres), cx1 = obs_cell(ox1[o], glo0, fi0, fres);
+        const int cy0 = obs_cell(oy0[o], glo1, fi1, fres), cy1 = obs_cell(oy1[o], glo1, fi1, fres);
+        for (int cy = cy0; cy <= cy1; cy++)
+          for (int cx = cx0; cx <= cx1; cx++) {
+            const bool inner = o < nb && cx > cx0 && cx < cx1 && cy > cy0 && cy < cy1;
+            put(cx, cy, inner ? (unsigned)OBS_FULL : (unsigned)OBS_PART);
+          }
+      }
+      CUDA_TRY(cudaMalloc((void**)&sp->d_fine, sizeof(unsigned) * fine.size()));
+      CUDA_TRY(cudaMemcpyAsync(sp->d_fine, fine.data(), sizeof(unsigned) * fine.size(), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      s.fine = sp->d_fine;
+      s.fnx = s.fny = fres;
+      s.finv0 = fi0;
+      s.finv1 = fi1;
+    }
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   s.use_grid = 1;
   s.gnx = gnx;
@@ -513,6 +695,7 @@ POMP_API int pomp_space_destroy(pomp_space* sp) {
   if (sp->d_cell_start) cudaFree(sp->d_cell_start);
   if (sp->d_cell_items) cudaFree(sp->d_cell_items);
   if (sp->d_cell_geom) cudaFree(sp->d_cell_geom);
+  if (sp->d_fine) cudaFree(sp->d_fine);
   if (sp->stream) cudaStreamDestroy(sp->stream);
   if (sp->overflow_h) cudaFreeHost(sp->overflow_h);
   delete sp;

@@ -24,8 +24,16 @@ struct SpaceDev {
   const int* cell_items;  // obstacle ids: boxes first, then n_boxes + circle id
   const double* cell_geom;  // the same items with their geometry inline, 4 doubles each: box (x0,y0,x1,y1) or
                             // circle (cx,cy,r,NaN) -- one dependent load less per candidate than id -> table
+  // fine occupancy map over the same domain, 2 bits per cell (16 cells per word): OBS_EMPTY -- no obstacle touches
+  // the cell; OBS_FULL -- the cell lies inside one box (every point of it is infeasible); OBS_PART -- look at the
+  // bucket.  Most point tests end here with ONE load from a table of ~1 MB (the bucket path is two dependent loads).
+  const unsigned* fine;     // NULL: no map
+  int fnx, fny;
+  double finv0, finv1;
   int* overflow;            // mapped pinned flag: an edge asked for more than POMP_MAX_EDGE_SAMPLES samples
 };
+
+constexpr int OBS_EMPTY = 0, OBS_FULL = 1, OBS_PART = 2;
 
 __host__ __device__ __forceinline__ int obs_cell(double x, double lo, double inv, int n) {
   double t = (x - lo) * inv;
@@ -48,20 +56,15 @@ __device__ __forceinline__ bool in_circle(const double* __restrict__ c, double p
   return sqrt(s) <= c[2];
 }
 
-__device__ __forceinline__ bool hits_obstacle(const SpaceDev& s, double px, double py) {
-  if (s.n_boxes + s.n_circles == 0) return false;
-  bool use_grid = s.use_grid && !(isnan(px) || isnan(py));
-  if (!use_grid) {
-    for (int o = 0; o < s.n_boxes; o++)
-      if (in_box(s.boxes + 4 * o, px, py)) return true;
-    for (int o = 0; o < s.n_circles; o++)
-      if (in_circle(s.circles + 3 * o, px, py)) return true;
-    return false;
-  }
-  if (px < s.glo0 || px > s.ghi0 || py < s.glo1 || py > s.ghi1) return false;  // outside every obstacle's box
+// bucket of the coarse obstacle grid that holds (px, py): its item range, then the scan (two steps, so that a caller
+// can put the range loads of several points in flight together)
+__device__ __forceinline__ void bucket_range(const SpaceDev& s, double px, double py, int& b, int& e) {
   int cx = obs_cell(px, s.glo0, s.ginv0, s.gnx), cy = obs_cell(py, s.glo1, s.ginv1, s.gny);
   int c = cy * s.gnx + cx;
-  int b = __ldg(s.cell_start + c), e = __ldg(s.cell_start + c + 1);
+  b = __ldg(s.cell_start + c);
+  e = __ldg(s.cell_start + c + 1);
+}
+__device__ __forceinline__ bool bucket_scan(const SpaceDev& s, int b, int e, double px, double py) {
   const double2* __restrict__ G = reinterpret_cast<const double2*>(s.cell_geom);
   for (int it = b; it < e; it++) {
     const double2 g0 = __ldg(G + 2 * it), g1 = __ldg(G + 2 * it + 1);
@@ -74,6 +77,43 @@ __device__ __forceinline__ bool hits_obstacle(const SpaceDev& s, double px, doub
     }
   }
   return false;
+}
+__device__ __forceinline__ bool hits_bucket(const SpaceDev& s, double px, double py) {
+  int b, e;
+  bucket_range(s, px, py, b, e);
+  return bucket_scan(s, b, e, px, py);
+}
+
+// classification of a point by the fine map: OBS_EMPTY / OBS_FULL decide the test, OBS_PART needs hits_bucket().
+// Only for spaces with use_grid and non-NaN coordinates (callers check); without a map everything is OBS_PART.
+__device__ __forceinline__ int obs_class(const SpaceDev& s, double px, double py) {
+  if (px < s.glo0 || px > s.ghi0 || py < s.glo1 || py > s.ghi1) return OBS_EMPTY;  // outside every obstacle's box
+  if (!s.fine) return OBS_PART;
+  const int cx = obs_cell(px, s.glo0, s.finv0, s.fnx), cy = obs_cell(py, s.glo1, s.finv1, s.fny);
+  const long long c = (long long)cy * s.fnx + cx;
+  return (int)((__ldg(s.fine + (c >> 4)) >> ((int)(c & 15) * 2)) & 3u);
+}
+
+__device__ __forceinline__ bool hits_obstacle(const SpaceDev& s, double px, double py) {
+  if (s.n_boxes + s.n_circles == 0) return false;
+  bool use_grid = s.use_grid && !(isnan(px) || isnan(py));
+  if (!use_grid) {
+    for (int o = 0; o < s.n_boxes; o++)
+      if (in_box(s.boxes + 4 * o, px, py)) return true;
+    for (int o = 0; o < s.n_circles; o++)
+      if (in_circle(s.circles + 3 * o, px, py)) return true;
+    return false;
+  }
+  const int cls = obs_class(s, px, py);
+  if (cls == OBS_EMPTY) return false;
+  if (cls == OBS_FULL) return true;
+  return hits_bucket(s, px, py);
+}
+
+__device__ __forceinline__ bool in_bounds(const SpaceDev& s, const double* x) {
+  for (int i = 0; i < s.dim; i++)
+    if (x[i] < s.lo[i] || x[i] > s.hi[i]) return false;
+  return true;
 }
 
 __device__ __forceinline__ bool feasible_pt(const SpaceDev& s, const double* x) {
@@ -109,6 +149,7 @@ struct pomp_space {
   int* d_cell_start = nullptr;
   int* d_cell_items = nullptr;
   double* d_cell_geom = nullptr;
+  unsigned* d_fine = nullptr;
   cudaStream_t stream = nullptr;
   pomp::DevBuf<double> in_a, in_b;
   pomp::DevBuf<int32_t> in_i;
