@@ -368,7 +368,22 @@ def run_extras(peak):
     ms_knn = time_cuda(lambda: nnr.knearest_device(nodes.data_ptr(), ne, 9, kidx.data_ptr(), kdst.data_ptr(), None, st),
                        reps=2, warm=1)
     ij = torch.stack([torch.arange(ne, device="cuda").repeat_interleave(8), kidx[:, 1:].reshape(-1)], 1).to(torch.int32).contiguous()
-    del kidx, kdst, nnr
+    del kidx, kdst
+    # BASELINE config 3 end to end, device-resident (csrc/roadmap.cu): node feasibility, 8-NN self-join, edge list,
+    # edge checks and the stable compaction of the feasible edges in one call; only the edge count returns
+    from pyoptimalmotionplanning_b200.roadmap import DeviceRoadmap
+    rmap = DeviceRoadmap(nnr, space)
+    rm_nodes = torch.empty(ne, dtype=torch.uint8, device="cuda")
+    rm_edges = torch.empty((ne * 8, 2), dtype=torch.int32, device="cuda")
+    rm_res = [0, 0]
+
+    def build_roadmap():
+        rm_res[0], rm_res[1] = rmap.build_device(8, 0.01, True, rm_nodes.data_ptr(), rm_edges.data_ptr(), ne * 8, st)
+    ms = time_cuda(build_roadmap, reps=2, warm=1)
+    out["roadmap_kink10k_4M_k8"] = {"ms": ms, "samples_per_s": ne / ms * 1e3, "candidate_edges": rm_res[1],
+                                    "feasible_edges": rm_res[0], "feasible_nodes": int(rm_nodes.sum().item()),
+                                    "candidate_edges_per_s": rm_res[1] / ms * 1e3}
+    del rmap, rm_nodes, rm_edges, nnr
     nedge = ij.shape[0]
     oki = torch.empty(nedge, dtype=torch.uint8, device="cuda")
     ms = time_cuda(lambda: space.edge_check_indexed_device(nodes.data_ptr(), ij.data_ptr(), nedge, 0.01, oki.data_ptr(), st),
@@ -503,6 +518,93 @@ def run_extras(peak):
         done = sum(rf.totalIters) - done0
         out["rrrt_bugtrap_lockstep_%dtrials" % T] = {"iters_per_s": done / dt, "per_trial_iters_per_s": done / T / dt,
                                                     "best_cost_trial0": rf.bestPathCost[0]}
+    return out
+
+
+def run_planner_extras():
+    """BASELINE configs 1, 4 and 5 at planner level: the UNMODIFIED reference planners (oracle/_ref copy) timed (a) on
+    the reference's own CPU path and (b) through install() + the CUDA drop-ins -- same seeds, same trees (asserted by
+    tests/test_gpu_dropins.py) -- and the lock-step sst* forest (csrc/sst.cu).  Bounded: a few seconds per leg."""
+    import contextlib
+    import io
+    import random
+    import pyoptimalmotionplanning_b200 as P
+    from oracle import refshim
+    out = {}
+    if not refshim.available():
+        return {"planners": "reference copy not staged (make -C oracle ref)"}
+    refshim.load()
+    from pomp.example_problems import geometric, dubins, doubleintegrator
+
+    def timed(make, iters, dropin):
+        if dropin:
+            P.install()
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                planner = make(dropin)
+                planner.planMore(20)
+                t0 = time.perf_counter()
+                for _ in range(iters // 10):
+                    planner.planMore(10)            # the reference harness's loop (planners/test.py:24)
+                dt = time.perf_counter() - t0
+        finally:
+            if dropin:
+                P.uninstall()
+        return iters / dt, planner
+
+    def rrrt(dropin):
+        random.seed(0)
+        prob = geometric.bugtrapTest()
+        kw = dict(nextStateSamplingRange=0.15)
+        if dropin:
+            kw.update(nearestNeighborMethod="b200", checker=P.make_checker(prob.configurationSpace, 0.01))
+        return prob.planner("r-rrt", **kw)
+
+    def aorrt(dropin):
+        random.seed(7)
+        prob = dubins.dubinsCarTest()
+        if not dropin:
+            return prob.planner("ao-rrt", numControlSamples=64)
+        planner = prob.planner("ao-rrt", numControlSamples=64, nearestNeighborMethod="b200",
+                               checker=P.make_checker(prob.configurationSpace, 0.01))
+        sel = planner.rrt.controlSelector
+        planner.setControlSelector(P.BatchedRandomControlSelector(sel.controlSpace, sel.metric, sel.numSamples))
+        return planner
+
+    def sst(dropin):
+        random.seed(7)
+        prob = doubleintegrator.doubleIntegratorTest()
+        kw = dict(selectionRadius=0.3, witnessRadius=0.3)
+        if dropin:
+            kw.update(nearestNeighborMethod="b200", checker=P.make_checker(prob.configurationSpace, 0.01))
+        return prob.planner("sst*", **kw)
+
+    for name, make, iters in (("config1_rrrt_bugtrap", rrrt, 1000), ("config4_aorrt64_dubins", aorrt, 300),
+                              ("config5_sststar_doubleintegrator", sst, 1000)):
+        try:
+            r_cpu, p_cpu = timed(make, iters, False)
+            r_gpu, p_gpu = timed(make, iters, True)
+            out[name] = {"reference_cpu_iters_per_s": r_cpu, "dropins_cuda_iters_per_s": r_gpu, "iters": iters,
+                         "same_best_cost": p_cpu.bestPathCost == p_gpu.bestPathCost,
+                         "note": "unmodified reference planner, 1 core; drop-ins: one launch + sync per call"}
+        except Exception as e:  # a planner-level extra must not take the bench down
+            out[name] = {"error": repr(e)[:200]}
+    # config 5 as it is meant to run: many seeded trials in lock step on the device
+    try:
+        from pyoptimalmotionplanning_b200.sst import SSTStarForest
+        prob = doubleintegrator.doubleIntegratorTest()
+        for T, its in ((256, 400), (1024, 200)):
+            with contextlib.redirect_stdout(io.StringIO()):
+                f = SSTStarForest(prob.controlSpace, prob.start, prob.goal, list(range(T)), prob.objective,
+                                  selectionRadius=0.3, witnessRadius=0.3)
+                f.planMore(50)
+                t0 = time.perf_counter()
+                f.planMore(its)
+                dt = time.perf_counter() - t0
+            out["config5_sststar_forest_%dtrials" % T] = {"iters_per_s": T * its / dt, "per_trial_iters_per_s": its / dt,
+                                                          "solved_trials": int(sum(1 for c in f.bestPathCost if c is not None and c < float("inf")))}
+    except Exception as e:
+        out["config5_sststar_forest"] = {"error": repr(e)[:200]}
     return out
 
 
@@ -860,13 +962,28 @@ def run_gpu(args):
         if world == 1:
             if not args.no_extras:
                 line["extras"] = run_extras(peak)
+                line["extras"].update(run_planner_extras())
             if not args.no_cpu:
                 cb = cpu_kdtree_run(2, 1, False)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "value_1core")}
+        keep = {k: line[k] for k in ("value", "ms_per_step", "e2e", "roofline") if k in line}
+        line = compact(line)
+        line.update(keep)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def compact(o):
+    """Floats to 5 significant digits (the line stays readable in a log tail); ints and strings untouched."""
+    if isinstance(o, float):
+        return float("%.5g" % o) if o == o and abs(o) != float("inf") else o
+    if isinstance(o, dict):
+        return {k: compact(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [compact(v) for v in o]
+    return o
 
 
 def main():

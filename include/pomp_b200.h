@@ -372,6 +372,21 @@ int pomp_forest_extend_multi_h(pomp_forest* f, pomp_space* s, int32_t n_iters, c
                                int32_t* n_done_h, int64_t* parent_h, double* xnew_h, double* edge_len_h,
                                int32_t* added_h);
 
+/* ---------------------------------------------------------------- device-resident roadmap ---------------- */
+/* k-nearest-neighbour roadmap over the node set of `nn` in space `s` (BASELINE config 3), every step a call of the
+   path: ConfigurationSpace.feasible per node (geometric.py:56-60) -> node_ok; NearestNeighbors.knearest(x, k+1) per
+   node (nearestneighbors.py:98-116; the node itself dropped); EpsilonEdgeChecker.feasible per candidate edge
+   (edgechecker.py:20-30); stable compaction of the feasible edges (node order, then neighbour rank) as index pairs
+   -- the (V, E) of TreePlanner.getRoadmap (kinodynamicplanner.py:211-238) without leaving the device.
+   undirected != 0: of a mutual pair only (min, max) is kept.  *n_edges_h may exceed cap (nothing is written beyond
+   cap; call again with more room).  Device pointers + stream in the first form, host buffers in the _h form. */
+int pomp_roadmap_build(pomp_nn* nn, pomp_space* s, int32_t k, double resolution, int32_t undirected,
+                       uint8_t* node_ok, int32_t* edges_out, int64_t cap, int64_t* n_edges_h,
+                       int64_t* n_candidates_h, void* stream);
+int pomp_roadmap_build_h(pomp_nn* nn, pomp_space* s, int32_t k, double resolution, int32_t undirected,
+                         uint8_t* node_ok_h, int32_t* edges_h, int64_t cap, int64_t* n_edges_h,
+                         int64_t* n_candidates_h);
+
 /* ---------------------------------------------------------------- EST projection-hash density ------------ */
 /* ESTWithProjections (kinodynamicplanner.py:746-868): nodes are hashed per projection basis b (<= 4 coordinates
    basis_idx[b][i] with scales basis_scale[b][i], rows padded to 4) to the cell key (int(x[k]*v))_k; density(x) =

@@ -154,6 +154,13 @@ struct pomp_space {
   pomp::DevBuf<double> in_a, in_b;
   pomp::DevBuf<int32_t> in_i;
   pomp::DevBuf<uint8_t> out_ok;
+  // scratch of pomp_roadmap_build (roadmap.cu)
+  pomp::DevBuf<int64_t> rm_kidx;
+  pomp::DevBuf<double> rm_kdist;
+  pomp::DevBuf<int32_t> rm_ij, rm_out;
+  pomp::DevBuf<uint8_t> rm_keep, rm_ok, rm_node_ok;
+  pomp::DevBuf<int> rm_flag, rm_pos;
+  pomp::DevBuf<long long> rm_scan;
   int* overflow_h = nullptr;  // host alias of dev.overflow
 };
 
