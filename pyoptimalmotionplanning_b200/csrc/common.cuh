@@ -55,6 +55,32 @@ extern std::atomic<uint64_t> g_realloc_gen;  // bumped by every DevBuf reallocat
     pomp::g_launches.fetch_add(1, std::memory_order_relaxed);          \
   } while (0)
 
+// Programmatic dependent launch: the kernel may be scheduled (and run up to its griddepcontrol.wait) while the previous
+// kernel of the stream is still draining -- hides the launch gap between the kernels of one step.  The kernel MUST
+// execute pomp::grid_dependency_wait() before it touches anything the previous kernel wrote.  Falls back to a plain
+// launch while the stream is being captured into a CUDA graph.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs == cudaStreamCaptureStatusNone ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                         \
+  do {                                                                             \
+    pomp::launch_pdl(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__); \
+    pomp::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
+  } while (0)
+
 #define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
 
 int validate_metric(const pomp_metric_desc* m);
@@ -107,6 +133,11 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---- device math ------------------------------------------------------------------------
 #define POMP_PI 3.141592653589793

@@ -40,7 +40,10 @@ namespace pomp {
 
 constexpr int WQ_EXT = 8;        // tabulated cells per axis (a shell's box is 3..5 cells wide)
 constexpr int WQ_WARPS = 8;      // warps per block
-constexpr int WQ_BULK_MIN = 7;   // W = 32: survivors in a slab from which the bulk merge beats single insertions
+#ifndef WQ_BULK
+#define WQ_BULK 7
+#endif
+constexpr int WQ_BULK_MIN = WQ_BULK;   // W = 32: survivors in a slab from which the bulk merge beats single insertions
 constexpr int WQ_DENSE = 24;     // candidates PER LANE in the first rows of the first shell beyond which the mean
                                  // density is taken to be useless (a cluster): the radius then comes from the
                                  // neighbours in sorted order instead

@@ -14,6 +14,11 @@ struct SortScratch {
   pomp::DevBuf<double> qsorted;
   pomp::DevBuf<long long> scan_tmp;
   bool ovf_zeroed = false;
+  // strip path (strip2d.cu): bucket counters that the kernels hand back ZEROED (the producer warp clears a tile's
+  // counters after reading them, the overflow pass clears the deferred count), so a step needs no memset launch
+  pomp::DevBuf<int> strip_ctrl;
+  bool strip_ctrl_clean = false;
+  size_t strip_ctrl_n = 0;
 };
 
 // ============================================================================ handle

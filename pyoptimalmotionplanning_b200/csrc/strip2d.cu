@@ -66,6 +66,27 @@ static int build_strip_index(pomp_nn* h, cudaStream_t st) {
   return POMP_OK;
 }
 
+// overflow pass of the strip path: grid-stride over the deferred list with the pruned traversal (the qlist branch of
+// grid_knn_fast_kernel), then the last block to finish moves the count to ctrl[2] and clears ctrl[1]
+static __global__ void __launch_bounds__(128)
+strip_overflow_kernel(GridDev g, const double* __restrict__ pts, long long n, const double* __restrict__ q,
+                      int64_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ out_cnt,
+                      const int* __restrict__ qlist, int* __restrict__ ctrl) {
+  grid_dependency_wait();
+  const long long cnt = *(volatile int*)(ctrl + 1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (long long)gridDim.x * blockDim.x)
+    knn_pruned_one<2, 1>(g, pts, n, nullptr, q, (long long)qlist[t], 1, out_idx, out_dist, out_cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned tk = atomicInc(reinterpret_cast<unsigned*>(ctrl + 3), gridDim.x - 1);  // wraps back to 0
+    if (tk == gridDim.x - 1) {
+      ctrl[2] = (int)cnt;
+      ctrl[1] = 0;
+    }
+  }
+}
+
 int pomp::strip_nearest(pomp_nn* h, const double* q, int64_t nq, int k, int64_t* idx, double* dist, int32_t* cnt,
                         cudaStream_t st) {
   (void)k;  // k == 1 (strip_eligible)
@@ -80,13 +101,22 @@ int pomp::strip_nearest(pomp_nn* h, const double* q, int64_t nq, int k, int64_t*
   const int Cs = (int)std::min<double>(1 << 17, ((long long)(2.0 * avg + 8.0) + 3) / 4 * 4);
   const size_t slots = (size_t)nt * ST_SUB * Cs;
   const size_t nctrl = (size_t)ST_CNT_STRIDE * (1 + (size_t)nt * ST_SUB);
-  POMP_TRY(S.counts.reserve(nctrl));
+  {
+    const int* before = S.strip_ctrl.p;
+    POMP_TRY(S.strip_ctrl.reserve(nctrl));
+    if (S.strip_ctrl.p != before || S.strip_ctrl_n != nctrl) S.strip_ctrl_clean = false;
+  }
   POMP_TRY(S.qsorted.reserve(slots * 4));  // 32-byte records
   POMP_TRY(S.ovf.reserve((size_t)nq + 2));
-  int* ctrl = S.counts.p;  // [0] unused, [1] deferred-to-pruned count, [ST_CNT_STRIDE (1 + t ST_SUB + sub)] bucket counters
+  // [1] deferred-to-pruned count, [2] its value at the end of the last step (statistics), [3] ticket of the overflow
+  // pass, [ST_CNT_STRIDE (1 + t ST_SUB + sub)] bucket counters
+  int* ctrl = S.strip_ctrl.p;
   int* l2 = S.ovf.p;
   StripQRec* qrec = reinterpret_cast<StripQRec*>(S.qsorted.p);
-  CUDA_TRY(cudaMemsetAsync(ctrl, 0, sizeof(int) * nctrl, st));
+  // the kernels leave the counters zeroed; only a fresh / resized buffer or a step that failed half-way is cleared here
+  if (!S.strip_ctrl_clean) CUDA_TRY(cudaMemsetAsync(ctrl, 0, sizeof(int) * nctrl, st));
+  S.strip_ctrl_clean = false;
+  S.strip_ctrl_n = nctrl;
   const double2* q2 = reinterpret_cast<const double2*>(q);
   LAUNCH(strip_qbucket_kernel, (int)((nq + 256 * ST_QPT - 1) / (256 * ST_QPT)), 256, 0, st, g, sd.nty, q2, (long long)nq,
          Cs, ctrl, qrec, l2);
@@ -101,17 +131,19 @@ int pomp::strip_nearest(pomp_nn* h, const double* q, int64_t nq, int k, int64_t*
   const size_t smem = ST_SMEM_HEAD + (size_t)nstages * strip_stage_bytes(cap);
   CUDA_TRY(cudaFuncSetAttribute(strip_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(h, st);
-  LAUNCH(strip_nn_kernel, sm_count(h->device), ST_THREADS, smem, st, g, sd, (const double*)h->d_pts, q2,
-         (const StripQRec*)qrec, ctrl, Cs, cap, nstages, idx, dist, cnt, l2, (int)h->strip_spin_ns,
-         (int)h->strip_probe);
+  LAUNCH_PDL(strip_nn_kernel, sm_count(h->device), ST_THREADS, smem, st, g, sd, (const double*)h->d_pts, q2,
+             (const StripQRec*)qrec, ctrl, Cs, cap, nstages, idx, dist, cnt, l2, (int)h->strip_spin_ns,
+             (int)h->strip_probe);
   prof_end(h, st);
   h->strip_launches++;
-  h->ovf_count_dev = ctrl + 1;
-  // ---- whatever neither the tiles nor the 5x5 retries could certify: pruned traversal
+  h->ovf_count_dev = ctrl + 2;
+  // ---- whatever neither the tiles nor the 5x5 retries could certify: pruned traversal; its last block hands the
+  // deferred counter back zeroed (copy in ctrl[2] for the statistics)
   const int oblocks = sm_count(h->device) * 4;
-  LAUNCH((grid_knn_fast_kernel<2, 1>), oblocks, 128, 0, st, g, h->d_pts, (long long)h->n_dev, h->skip_ptr(), q,
-         (long long)nq, (const int*)nullptr, 1, idx, dist, cnt, (const int*)l2, (const int*)(ctrl + 1));
+  LAUNCH_PDL(strip_overflow_kernel, oblocks, 128, 0, st, g, (const double*)h->d_pts, (long long)h->n_dev, q, idx, dist,
+             cnt, (const int*)l2, ctrl);
   CHECK_LAUNCH();
   S.ovf_zeroed = false;
+  S.strip_ctrl_clean = true;
   return POMP_OK;
 }

@@ -208,6 +208,8 @@ strip_nn_kernel(GridDev g, StripDev sd, const double* __restrict__ pts, const do
     fence_mbar_init();
   }
   __syncthreads();
+  grid_dependency_wait();      // launched programmatically behind the query bucketing: its counters and records
+  grid_launch_dependents();    // the overflow pass may be scheduled; it waits for this grid to complete
 
   if (warp == ST_MAX_STAGES * ST_WG) {
     // ---------------- producer warp.  Metadata of 32 tiles is fetched at once (one lane each: the latency of the
@@ -226,7 +228,13 @@ strip_nn_kernel(GridDev g, StripDev sd, const double* __restrict__ pts, const do
       if (valid) {
         int c[ST_SUB];
 #pragma unroll
-        for (int j = 0; j < ST_SUB; j++) c[j] = __ldg(ctrl + ST_CNT_STRIDE * (1 + (long long)tile * ST_SUB + j));
+        for (int j = 0; j < ST_SUB; j++) {
+          // read and clear: the counters go back to the host side zeroed (no memset launch per step); plain
+          // loads -- the read-only path must not see a location this kernel writes
+          int* cp = ctrl + ST_CNT_STRIDE * (1 + (long long)tile * ST_SUB + j);
+          c[j] = __ldcg(cp);
+          if (c[j]) *cp = 0;
+        }
         info = __ldg(sd.tile_info + tile);
 #pragma unroll
         for (int j = 0; j < ST_SUB; j++) pre[j + 1] = pre[j] + min(c[j], Cs);
