@@ -852,6 +852,34 @@ def run_gpu(args):
     e2e_idx_s = float(t.item())
     assert torch.equal(idx_h[:, 0], idx.cpu())
 
+    # ---- the copy floor of this box for the e2e call: the same bytes (queries in, results out) as plain pinned copies
+    # on two streams at once, all ranks together (on a multi-GPU box the ranks share the host's PCIe / memory system)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    q_land = torch.empty_like(q_dev)
+    res_dev = torch.empty((qs, K * 2), dtype=torch.float64, device="cuda")
+    res_h = torch.empty((qs, K * 2), dtype=torch.float64).pin_memory()
+
+    def copy_step():
+        with torch.cuda.stream(s_in):
+            q_land.copy_(q_slice_h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            res_h.copy_(res_dev, non_blocking=True)
+    for _ in range(3):
+        copy_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        copy_step()
+    torch.cuda.synchronize()
+    barrier()
+    copy_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([copy_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_s = float(t.item())
+    del q_land, res_dev, res_h
+
     # ---- N > 1: the HEADLINE is the north-star split: ONE node set of 2^24 points sharded spatially
     # over the N GPUs (slabs of the last coordinate + halo copies), 2^20 queries per GPU routed to the owning GPU
     # with an all-to-all over NCCL/NVLink, answered locally with a certificate, packed (distance, index) records
@@ -947,7 +975,9 @@ def run_gpu(args):
                              "traffic": measured_traffic("grid_knn_D2_k1")},
                 "e2e": {"value": world * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": qs * DIM * 8 * world,
                         "d2h_bytes_per_step": qs * K * 16 * world, "ms_per_step": e2e_s * 1e3,
-                        "api": "pomp_nn_nearest_h (pinned host buffers; H2D / search / D2H pipelined over chunks, chunk searches replayed as CUDA graphs)"},
+                        "api": "pomp_nn_nearest_h (pinned host buffers; H2D / search / D2H pipelined over chunks, chunk searches replayed as CUDA graphs)",
+                        "copy_floor_ms": copy_s * 1e3,
+                        "copy_floor_note": "the same bytes as plain pinned H2D + D2H copies on two streams, all ranks at once, no search"},
                 "e2e_index_only": {"value": world * nq / e2e_idx_s, "unit": "queries/s", "ms_per_step": e2e_idx_s * 1e3,
                                    "d2h_bytes_per_step": qs * K * 8 * world,
                                    "note": "same call with dist_h = NULL (NearestNeighbors.nearest returns the node only)"},

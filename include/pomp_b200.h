@@ -114,8 +114,22 @@ int pomp_nn_set_mask_h(pomp_nn* h, const uint8_t* reject_mask_h, int64_t n);
 /* CostSpaceRRT.updateBestCost mutates the metric in place (kinodynamicplanner.py:1059-1077) */
 int pomp_nn_update_metric(pomp_nn* h, const pomp_metric_desc* metric);
 int64_t pomp_nn_size(const pomp_nn* h);
-/* tuning knobs: "grid_min_points" / "grid_min_queries" (below: brute-force kernels), "points_per_cell",
-   "sort_queries", "max_tail", "profile" */
+/* Tuning knobs (every name pomp_nn_set_param accepts; defaults in nn_handle.cuh; none of them changes an answer):
+     regime        "grid_min_points" (16384), "grid_min_queries" (64): below either, the brute-force kernels;
+                   "max_tail" (2048): points appended since the last index build before it is rebuilt;
+                   "points_per_cell" (0 = 1.5 / 2 / 4 by dimension): target cell occupancy, rebuilds the index;
+                   "periodic_axes" (1): SO(2) components of a product metric become wrap-around grid axes
+     query sort    "sort_queries" (1), "sort_min_queries" (32768), "sort_shift": bucket sort of large batches by
+                   coarse home bin; "overlap_chunks" (1), "overlap_min_queries": sort of chunk c+1 on a second
+                   stream (measured slower, kept off)
+     kernel choice "strip_search" (1), "strip_min_per_tile", "strip_spin_ns", "strip_probe": streaming kernel for dense
+                   2-D nearest() batches; "block_search" (1; 2 = also in 3-D), "block_need": fixed block of cells +
+                   certificate in 2-D; "warp_search" (1 = where it wins, 2 = always, 0 = never), "warp_lanes" (32; 8,
+                   16), "warp_need": the warp-per-query shell kernel; "se2_fast" (1): compile-time SE(2) kernel;
+                   "bf_tiled" (1): shared-memory tiled brute force for Euclidean k = 1 batches
+     host pipeline "pipeline_chunks" (6), "pipeline_shape" (1 = triangle), "use_graphs" (1): the *_h entry points
+     measurement   "profile" (0): CUDA events around the dominant search kernel, read back with
+                   pomp_nn_get_stat("search_kernel_ms" / "search_kernel_launches") */
 int pomp_nn_set_param(pomp_nn* h, const char* name, double value);
 /* read-outs: "search_kernel_ms" / "search_kernel_launches" (CUDA-event time of the dominant search
    kernel since set_param("profile",1); call after synchronising), "n_cells", "n_indexed", "grid_axes" */
