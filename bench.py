@@ -993,7 +993,7 @@ def run_gpu(args):
             line["ms_per_step"] = sharded["ms_per_step"]
             line["e2e"] = {"value": world * nq / sharded["e2e_s"], "unit": "queries/s",
                            "h2d_bytes_per_step": qs * DIM * 8 * world, "d2h_bytes_per_step": qs * K * 16 * world,
-                           "ms_per_step": sharded["e2e_s"] * 1e3,
+                           "ms_per_step": sharded["e2e_s"] * 1e3, "copy_floor_ms": copy_s * 1e3,
                            "api": "SpatialShardedNearestNeighbors.knearest_fast (pinned host queries in, host results out)"}
             line.pop("e2e_index_only", None)
             line["node_sharded"] = sharded
