@@ -369,6 +369,17 @@ def run_extras(peak):
                        reps=2, warm=1)
     ij = torch.stack([torch.arange(ne, device="cuda").repeat_interleave(8), kidx[:, 1:].reshape(-1)], 1).to(torch.int32).contiguous()
     del kidx, kdst
+    # the same edge set with the node count known: feasibility once per node, the edges gather the flags
+    nok = torch.empty(ne, dtype=torch.uint8, device="cuda")
+    ok_a2 = torch.empty(ne * 8, dtype=torch.uint8, device="cuda")
+    ms = time_cuda(lambda: space.edge_check_indexed_nodes_device(nodes.data_ptr(), ne, ij.data_ptr(), ne * 8, 0.01,
+                                                                 nok.data_ptr(), ok_a2.data_ptr(), st))
+    ok_a1 = torch.empty(ne * 8, dtype=torch.uint8, device="cuda")
+    space.edge_check_indexed_device(nodes.data_ptr(), ij.data_ptr(), ne * 8, 0.01, ok_a1.data_ptr(), st)
+    out["edge_checks_indexed_8nn_nodeflags_res0.01"] = {"edges_per_s": ne * 8 / ms * 1e3, "ms": ms,
+                                                        "hbm_frac": (ne * 8 * 41) / (ms * 1e-3) / 1e9 / peak,
+                                                        "same_as_plain_call": bool(torch.equal(ok_a1, ok_a2))}
+    del nok, ok_a1, ok_a2
     # BASELINE config 3 end to end, device-resident (csrc/roadmap.cu): node feasibility, 8-NN self-join, edge list,
     # edge checks and the stable compaction of the feasible edges in one call; only the edge count returns
     from pyoptimalmotionplanning_b200.roadmap import DeviceRoadmap

@@ -260,6 +260,12 @@ int pomp_edge_check_h(pomp_space* s, const double* a_h, const double* b_h, int64
 /* same, edges given as index pairs ij[n_edges][2] into a roadmap node array nodes[*][dim] */
 int pomp_edge_check_indexed(pomp_space* s, const double* nodes, const int32_t* ij, int64_t n_edges,
                             double resolution, uint8_t* ok, void* stream);
+/* same with the node count known: ConfigurationSpace.feasible (geometric.py:56-60) is evaluated ONCE per node into
+   node_ok[n_nodes] (device; returned to the caller) and the edges only gather the two flags and test their interior
+   samples -- the result is the same conjunction (edgechecker.py:20-30); in a k-NN roadmap every node is an endpoint
+   of ~2k edges */
+int pomp_edge_check_indexed_nodes(pomp_space* s, const double* nodes, int64_t n_nodes, const int32_t* ij,
+                                  int64_t n_edges, double resolution, uint8_t* node_ok, uint8_t* ok, void* stream);
 /* PiecewiseLinearInterpolator / GeodesicInterpolator edges (interpolators.py:37-48,73-102):
    path p has waypoints [path_offsets[p], path_offsets[p+1]) of `waypoints` (row-major x dim);
    length / interpolation follow `geodesic` (EUCLIDEAN or GEODESIC_PRODUCT). */

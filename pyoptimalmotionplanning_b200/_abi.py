@@ -98,6 +98,7 @@ SIGNATURES = {
     "pomp_shard_unpack_p2p": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "pomp_shard_gather_deferred": (C.c_int, [_P, _I32, _P, _P, _I64, _P, _P, _P]),
     "pomp_shard_scatter_deferred": (C.c_int, [_P, _P, _I32, _P, _P, _I64, _P, _P, _P]),
+    "pomp_edge_check_indexed_nodes": (C.c_int, [_P, _P, _I64, _P, _I64, C.c_double, _P, _P, _P]),
     "pomp_roadmap_build": (C.c_int, [_P, _P, _I32, C.c_double, _I32, _P, _P, _I64, _P, _P, _P]),
     "pomp_roadmap_build_h": (C.c_int, [_P, _P, _I32, C.c_double, _I32, _P, _P, _I64, _P, _P]),
     "pomp_est_create": (C.c_int, [_I32, _I32, _P, _P, _P, _P, C.c_int, C.POINTER(_P)]),

@@ -296,6 +296,15 @@ class CudaSpace(object):
                                                          float(resolution), C.c_void_p(ok_ptr),
                                                          C.c_void_p(stream or 0)))
 
+    def edge_check_indexed_nodes_device(self, nodes_ptr, n_nodes, ij_ptr, n_edges, resolution, node_ok_ptr, ok_ptr,
+                                        stream=None):
+        """Roadmap edges with the node count known: feasibility once per node (flags returned in node_ok), the edges
+        gather the flags and test their interior samples."""
+        check(self.lib, self.lib.pomp_edge_check_indexed_nodes(self._h, C.c_void_p(nodes_ptr), n_nodes,
+                                                               C.c_void_p(ij_ptr), n_edges, float(resolution),
+                                                               C.c_void_p(node_ok_ptr), C.c_void_p(ok_ptr),
+                                                               C.c_void_p(stream or 0)))
+
 
 class CudaDynamics(object):
     """Batched nextState / fused control selection (pomp_next_state*, pomp_select_control*)."""

@@ -103,11 +103,13 @@ POMP_API int pomp_roadmap_build(pomp_nn* nn, pomp_space* s, int32_t k, double re
   POMP_TRY(s->rm_flag.reserve((size_t)ne + 1));
   POMP_TRY(s->rm_pos.reserve((size_t)ne + 1));
   POMP_TRY(s->rm_scan.reserve(scan_scratch_elems(ne)));
-  if (node_ok) POMP_TRY(pomp_feasible(s, nn->d_pts, n, node_ok, stream));
+  POMP_TRY(s->rm_node_ok.reserve((size_t)n));
+  uint8_t* nok = node_ok ? node_ok : s->rm_node_ok.p;
   POMP_TRY(pomp_nn_knearest(nn, nn->d_pts, n, k1, s->rm_kidx.p, s->rm_kdist.p, nullptr, stream));
   LAUNCH(roadmap_edges_kernel, (int)((n + 255) / 256), 256, 0, st, s->rm_kidx.p, (long long)n, k1, undirected,
          s->rm_ij.p, s->rm_keep.p);
-  POMP_TRY(pomp_edge_check_indexed(s, nn->d_pts, s->rm_ij.p, ne, resolution, s->rm_ok.p, stream));
+  // node feasibility once per node; the edges gather the flags and test their interior samples only
+  POMP_TRY(pomp_edge_check_indexed_nodes(s, nn->d_pts, n, s->rm_ij.p, ne, resolution, nok, s->rm_ok.p, stream));
   const int eb = (int)((ne + 255) / 256);
   LAUNCH(roadmap_flags_kernel, eb, 256, 0, st, s->rm_keep.p, s->rm_ok.p, (long long)ne, s->rm_flag.p);
   POMP_TRY(exclusive_scan<int>(s->rm_flag.p, ne, s->rm_pos.p, s->rm_scan.p, st));

@@ -129,8 +129,11 @@ __device__ __forceinline__ void edge_queue_pop64(const SpaceDev& s, EdgeQueue& Q
   __syncwarp();
 }
 
+// ep_known: -1 = test the endpoints here; 0 / 1 = ConfigurationSpace.feasible of BOTH endpoints is already known
+// (roadmap edges: every node is an endpoint of ~2k edges, its test is done once per node instead)
 __device__ __forceinline__ bool edge_batch_warp2d(const SpaceDev& s, double2 a, double2 b, bool valid, double res,
-                                                  unsigned* failbits /* one word per warp, shared */, EdgeQueue& Q) {
+                                                  unsigned* failbits /* one word per warp, shared */, EdgeQueue& Q,
+                                                  int ep_known = -1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double pa[2] = {a.x, a.y}, pb[2] = {b.x, b.y};
@@ -146,13 +149,13 @@ __device__ __forceinline__ bool edge_batch_warp2d(const SpaceDev& s, double2 a, 
   const bool mapped = s.use_grid != 0;
   // BoxSet.contains on both coordinates (sets.py:177-182); NaN passes, as in Python
   auto inb = [&](double x0, double x1) { return !(x0 < s.lo[0] || x0 > s.hi[0] || x1 < s.lo[1] || x1 > s.hi[1]); };
-  bool alive = valid && k >= 0 && inb(pa[0], pa[1]) && inb(pb[0], pb[1]);
+  bool alive = valid && k >= 0 && (ep_known >= 0 ? ep_known != 0 : (inb(pa[0], pa[1]) && inb(pb[0], pb[1])));
   if (__all_sync(FULL, !valid || (k >= 0 && k <= 2))) {
     // a warp of short edges (roadmap edges to near neighbours: one or two samples each): the queue machinery costs
     // more than it saves, every lane walks its own edge
     bool okv = alive;
-    if (okv) okv = !hits_obstacle(s, s.od0 ? pa[1] : pa[0], s.od1 ? pa[1] : pa[0]);
-    if (okv) okv = !hits_obstacle(s, s.od0 ? pb[1] : pb[0], s.od1 ? pb[1] : pb[0]);
+    if (okv && ep_known < 0) okv = !hits_obstacle(s, s.od0 ? pa[1] : pa[0], s.od1 ? pa[1] : pa[0]);
+    if (okv && ep_known < 0) okv = !hits_obstacle(s, s.od0 ? pb[1] : pb[0], s.od1 ? pb[1] : pb[0]);
     for (int i = 0; okv && i < (int)k; i++) {
       const double u = (double)(i + 1) / (double)(k + 2);
       const double x0 = pa[0] + u * dx, x1 = pa[1] + u * dy;
@@ -174,7 +177,7 @@ __device__ __forceinline__ bool edge_batch_warp2d(const SpaceDev& s, double2 a, 
       const double px = s.od0 ? e1 : e0, py = s.od1 ? e1 : e0;
       epx[h] = px;
       epy[h] = py;
-      if (alive) {
+      if (alive && ep_known < 0) {
         if (!mapped || isnan(px) || isnan(py)) {
           if (hits_obstacle(s, px, py)) alive = false;
         } else {
@@ -284,18 +287,21 @@ edge_check_warp2d_kernel(SpaceDev s, const double* __restrict__ a, const double*
 
 __global__ void __launch_bounds__(128)
 edge_check_indexed_warp2d_kernel(SpaceDev s, const double* __restrict__ nodes, const int* __restrict__ ij,
-                                 long long n, double res, uint8_t* __restrict__ ok) {
+                                 long long n, double res, uint8_t* __restrict__ ok,
+                                 const uint8_t* __restrict__ node_ok) {
   __shared__ unsigned failbits[4];
   __shared__ EdgeQueue queues[4];
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = e < n;
+  int epk = -1;
   double2 va = make_double2(0, 0), vb = make_double2(0, 0);
   if (valid) {
     int2 pr = __ldg(reinterpret_cast<const int2*>(ij) + e);
     va = __ldg(reinterpret_cast<const double2*>(nodes) + pr.x);
     vb = __ldg(reinterpret_cast<const double2*>(nodes) + pr.y);
+    if (node_ok) epk = (__ldg(node_ok + pr.x) && __ldg(node_ok + pr.y)) ? 1 : 0;
   }
-  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5], queues[threadIdx.x >> 5]);
+  bool r = edge_batch_warp2d(s, va, vb, valid, res, &failbits[threadIdx.x >> 5], queues[threadIdx.x >> 5], epk);
   if (valid) ok[e] = r ? 1 : 0;
 }
 
@@ -761,9 +767,30 @@ POMP_API int pomp_edge_check_indexed(pomp_space* sp, const double* nodes, const 
   int blocks = (int)((n_edges + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   if (sp->dev.dim == 2)
-    LAUNCH(edge_check_indexed_warp2d_kernel, blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok);
+    LAUNCH(edge_check_indexed_warp2d_kernel, blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok,
+           (const uint8_t*)nullptr);
   else
     LAUNCH((edge_check_indexed_kernel<0>), blocks, 128, 0, st, sp->dev, nodes, ij, (long long)n_edges, resolution, ok);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+// The same with the node count known: ConfigurationSpace.feasible is evaluated ONCE per node (node_ok[n_nodes], device,
+// caller-provided scratch that also returns the flags) and the edges only gather the two flags and test their interior
+// samples.  In a k-NN roadmap every node is an endpoint of ~2k edges.
+POMP_API int pomp_edge_check_indexed_nodes(pomp_space* sp, const double* nodes, int64_t n_nodes, const int32_t* ij,
+                                           int64_t n_edges, double resolution, uint8_t* node_ok, uint8_t* ok,
+                                           void* stream) {
+  POMP_REQUIRE(sp && n_nodes >= 0 && n_edges >= 0 && (n_nodes == 0 || (nodes && node_ok)) && (n_edges == 0 || (ij && ok)),
+               "bad arguments to pomp_edge_check_indexed_nodes");
+  POMP_REQUIRE(resolution > 0.0, "resolution must be positive");
+  DeviceGuard g(sp->device);
+  if (!g.ok) return POMP_ERR_CUDA;
+  if (n_nodes > 0) POMP_TRY(pomp_feasible(sp, nodes, n_nodes, node_ok, stream));
+  if (n_edges == 0) return POMP_OK;
+  if (sp->dev.dim != 2) return pomp_edge_check_indexed(sp, nodes, ij, n_edges, resolution, ok, stream);
+  LAUNCH(edge_check_indexed_warp2d_kernel, (int)((n_edges + 127) / 128), 128, 0, (cudaStream_t)stream, sp->dev, nodes,
+         ij, (long long)n_edges, resolution, ok, (const uint8_t*)node_ok);
   CHECK_LAUNCH();
   return POMP_OK;
 }

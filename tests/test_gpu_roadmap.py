@@ -102,3 +102,32 @@ def test_forest_results_csv_on_cuda_has_the_reference_layout(tmp_path):
     t0 = [(int(r[1]), float(r[3])) for r in parsed if r[0] == "4"]
     want = [(c[0], c[1]) for c in g1["change_points"] if c[0] <= 700]
     assert t0[:-1] == want and t0[-1] == (700, want[-1][1])
+
+
+def test_indexed_edges_with_node_flags_equal_plain_indexed_edges():
+    """pomp_edge_check_indexed_nodes (feasibility once per node, the edges gather the flags) returns the booleans of
+    pomp_edge_check_indexed and of the oracle -- short roadmap edges, long edges, infeasible and out-of-bounds nodes."""
+    import torch
+    from pyoptimalmotionplanning_b200.backend import CudaSpace
+    rng = np.random.default_rng(21)
+    sp = _field(rng, 800)
+    space = CudaSpace(sp, 0)
+    nodes = rng.random((50000, 2)) * 1.04 - 0.02                   # a few nodes outside the bounds
+    ij = np.concatenate([np.stack([np.arange(50000), (np.arange(50000) + 1) % 50000], 1),        # long edges
+                         np.stack([rng.integers(0, 50000, 100000), rng.integers(0, 50000, 100000)], 1)]).astype(np.int32)
+    near = np.argsort(nodes[:2000, 0])                              # short edges between x-neighbours
+    ij = np.concatenate([ij, np.stack([near[:-1], near[1:]], 1).astype(np.int32)])
+    d_nodes, d_ij = torch.from_numpy(nodes).cuda(), torch.from_numpy(ij).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    for res in (0.01, 0.003):
+        ok1 = torch.empty(len(ij), dtype=torch.uint8, device="cuda")
+        ok2 = torch.empty(len(ij), dtype=torch.uint8, device="cuda")
+        nok = torch.empty(len(nodes), dtype=torch.uint8, device="cuda")
+        space.edge_check_indexed_device(d_nodes.data_ptr(), d_ij.data_ptr(), len(ij), res, ok1.data_ptr(), st)
+        space.edge_check_indexed_nodes_device(d_nodes.data_ptr(), len(nodes), d_ij.data_ptr(), len(ij), res,
+                                              nok.data_ptr(), ok2.data_ptr(), st)
+        torch.cuda.synchronize()
+        want = oracle.edge_check_indexed(sp, nodes, ij, res)
+        assert (ok1.cpu().numpy() == want).all()
+        assert (ok2.cpu().numpy() == want).all()
+        assert (nok.cpu().numpy() == oracle.feasible(sp, nodes)).all()
