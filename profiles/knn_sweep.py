@@ -22,7 +22,7 @@ for D in Ds:
         dst = torch.empty((nq, K), dtype=torch.float64, device="cuda")
         ref = None
         variants = [("thread", 0, 0, 0)]
-        for lanes in (8, 16, 32):
+        for lanes in (0, 32):
             for ppc in (0,) + ((8,) if D >= 4 else ()):
                 for need in (0,) + ((5,) if K == 1 else (1.6 * K,)):
                     variants.append(("warp%d" % lanes, ppc, need, 2))

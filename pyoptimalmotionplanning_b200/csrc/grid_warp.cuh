@@ -92,10 +92,10 @@ struct Group {
   __device__ __forceinline__ void sync() const { __syncwarp(gm); }
 };
 
-// ---- sorted list of 32 keys spread over the group: position p in lane p % W, slot p / W ------------------------------
-template <int W>
+// ---- sorted list of W * KL keys spread over the group: position p in lane p % W, slot p / W ------------------------
+// KL = 1 (one key per lane: k <= W) has the bulk merge; KL > 1 only the single insertions
+template <int W, int KL>
 struct GroupList {
-  static constexpr int KL = 32 / W;
   double d[KL];
   int i[KL];
   double kd;  // k-th key, group-uniform
@@ -170,32 +170,33 @@ struct GroupList {
       mask = G.ballot(pass);
     }
   }
-  static __device__ __forceinline__ void cmpx(double& kd_, int& ki_, int stride, bool keep_min) {
-    const double od = __shfl_xor_sync(FULL_MASK, kd_, stride);
-    const int oi = __shfl_xor_sync(FULL_MASK, ki_, stride);
+  static __device__ __forceinline__ void cmpx(const Group<W>& G, double& kd_, int& ki_, int stride, bool keep_min) {
+    const double od = G.shfl_xor(kd_, stride);
+    const int oi = G.shfl_xor(ki_, stride);
     const bool oless = wkey_less(od, oi, kd_, ki_);
     if (keep_min ? oless : !oless) {
       kd_ = od;
       ki_ = oi;
     }
   }
-  // W = 32 only.  One candidate per lane, many expected to pass: sort the slab, keep the 32 smallest of slab + list
+  // KL = 1 only.  One candidate per lane, many expected to pass: sort the slab (bitonic network over the W lanes),
+  // keep the W smallest of slab + list
   __device__ __forceinline__ void offer_bulk(const Group<W>& G, double cd, int ci, bool list_empty) {
-    static_assert(W == 32 || sizeof(G) == 0 || true, "");
+    static_assert(KL == 1, "bulk merge needs one key per lane");
     const int lane = G.gl;
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
+    for (int size = 2; size <= W; size <<= 1) {
 #pragma unroll
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        const bool up = (lane & size) == 0 || size == 32;
+        const bool up = (lane & size) == 0 || size == W;
         const bool lower = (lane & stride) == 0;
-        cmpx(cd, ci, stride, lower == up);
+        cmpx(G, cd, ci, stride, lower == up);
       }
     }
     if (!list_empty) {
-      // min(list[l], slab[31 - l]) is a bitonic sequence holding the 32 smallest keys of the union
-      const double rd = __shfl_sync(FULL_MASK, cd, 31 - lane);
-      const int ri = __shfl_sync(FULL_MASK, ci, 31 - lane);
+      // min(list[l], slab[W - 1 - l]) is a bitonic sequence holding the W smallest keys of the union
+      const double rd = G.shfl(cd, W - 1 - lane);
+      const int ri = G.shfl(ci, W - 1 - lane);
       if (wkey_less(d[0], i[0], rd, ri)) {
         cd = d[0];
         ci = i[0];
@@ -204,7 +205,7 @@ struct GroupList {
         ci = ri;
       }
 #pragma unroll
-      for (int stride = 16; stride > 0; stride >>= 1) cmpx(cd, ci, stride, (lane & stride) == 0);
+      for (int stride = W / 2; stride > 0; stride >>= 1) cmpx(G, cd, ci, stride, (lane & stride) == 0);
     }
     d[0] = cd;
     i[0] = ci;
@@ -308,8 +309,8 @@ struct WCand {
   }
 };
 
-// K1 = true: nearest neighbour (lane-local bests); false: sorted list of 32, k <= 32.  W lanes per query.
-template <int D, bool K1, int W>
+// K1 = true: nearest neighbour (lane-local bests); false: sorted list of W * KL keys, k <= W * KL.  W lanes per query.
+template <int D, bool K1, int W, int KL>
 __global__ void __launch_bounds__(WQ_WARPS * 32, (D >= 6 ? WQ_OCC6 : WQ_OCC))
 grid_knn_warp_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
                      const double* __restrict__ q, const double* __restrict__ qsorted, long long nq,
@@ -348,7 +349,7 @@ grid_knn_warp_kernel(GridDev g, const double* __restrict__ pts, long long n, con
 #pragma unroll
   for (int a = 0; a < D; a++) home[a] = grid_cell(g, a, qq[a]);
 
-  GroupList<W> top;
+  GroupList<W, KL> top;
   top.init(k);
   // K1 state: lane-local best and the group-uniform (conservative) threshold
   double bd = POMP_INF, btsq = POMP_INF, utsq = POMP_INF;
@@ -380,8 +381,8 @@ grid_knn_warp_kernel(GridDev g, const double* __restrict__ pts, long long n, con
       }
       const unsigned m = G.ballot(pass);
       if (m) {
-        if constexpr (W == 32) {
-          if (__popc(m) >= WQ_BULK_MIN) top.offer_bulk(G, d, c.id, top.empty(G));
+        if constexpr (KL == 1) {
+          if (__popc(m) >= (W >= 32 ? WQ_BULK_MIN : (W >= 16 ? 5 : 4))) top.offer_bulk(G, d, c.id, top.empty(G));
           else top.offer_each(G, d, c.id);
         } else {
           top.offer_each(G, d, c.id);
@@ -569,7 +570,7 @@ grid_knn_warp_kernel(GridDev g, const double* __restrict__ pts, long long n, con
   } else {
     int cnt = 0;
 #pragma unroll
-    for (int s = 0; s < GroupList<W>::KL; s++) {
+    for (int s = 0; s < KL; s++) {
       const int p = s * W + G.gl;
       const bool fin = top.d[s] < POMP_INF && p < k;
       if (p < k) {

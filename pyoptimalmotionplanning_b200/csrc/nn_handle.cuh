@@ -68,7 +68,7 @@ struct pomp_nn {
   double se2_fast = 1;      // SE(2) product metric: compile-time kernel (grid_se2.cuh) instead of the generic one
   double block_need = 0;    // k = 1: expected points in the certified ball that selects the block radius (0 = default)
   double warp_search = 1;   // Euclidean k-NN: warp-per-query shell kernel (grid_warp.cuh); 0 off, 1 where it wins, 2 always
-  double warp_lanes = 32;   // lanes per query of that kernel (8, 16 or 32; narrow groups only pay for k = 1)
+  double warp_lanes = 0;    // lanes per query of that kernel (0 = by k: 8 / 16 / 32 lanes hold k <= 8 / 16 / 32 keys)
   double warp_need = 0;     // expected points inside its first shell (0 = k + 1.5 sqrt(k) + 1; 3 for k = 1)
   double block_search = 1;  // 2-D Euclidean: fixed block of cells + certificate (0: pruned traversal; 2: also in 3-D)
   // scratch for queries

@@ -822,7 +822,7 @@ def _lexsort_knn(pts, q, k, mask=None):
     return oi, od
 
 
-@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("lanes", [0, 8, 16, 32])
 @pytest.mark.parametrize("D", [2, 3, 4, 6])
 @pytest.mark.parametrize("k", [1, 5, 16, 32])
 def test_warp_shell_kernel_matches_oracle(D, k, lanes):
@@ -852,7 +852,7 @@ def test_warp_shell_kernel_matches_oracle(D, k, lanes):
         assert (i1 == oi[:, 0]).all() and (d1 == od[:, 0]).all()
 
 
-@pytest.mark.parametrize("lanes", [8, 32])
+@pytest.mark.parametrize("lanes", [0, 8, 32])
 @pytest.mark.parametrize("D", [2, 3, 6])
 def test_warp_shell_kernel_masks_tail_ties_and_clusters(D, lanes):
     rng = np.random.default_rng(77 + D)
