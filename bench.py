@@ -255,10 +255,13 @@ def workload_config(gpus):
             "points": 1 << LOG2_N, "queries_per_gpu": 1 << LOG2_Q, "global_queries": gpus << LOG2_Q, "dim": DIM, "k": K,
             "l2": "inputs (%.0f MB of points) exceed the 126 MB L2; no explicit flush" % ((1 << LOG2_N) * DIM * 8 / 1e6),
             "parallelism": "1 GPU" if gpus == 1 else
-                           "node set (2^%d points) sharded spatially over %d GPUs (slabs + halo); queries routed to the "
-                           "owning GPU with all_to_all (NCCL), packed (distance, index) records returned with all_to_all, "
-                           "uncertified remainder through an all_gather fallback; replicated-index number under "
-                           "replicated_index" % (LOG2_N, gpus)}
+                           "node set (2^%d points) sharded spatially over %d GPUs (slabs + halo); every query routed to "
+                           "the owning GPU and its packed (distance, index) record returned, both by NVLink stores from "
+                           "the routing / finalize kernels into peer memory (node_sharded.exchange = p2p; NCCL all_to_all "
+                           "when symmetric memory is unavailable), two device barriers and one all_reduce (deferred "
+                           "count) per batch, uncertified remainder through an all_gather fallback; batches streamed "
+                           "(batch i is validated on the host after batch i+1 was issued); replicated-index number "
+                           "under replicated_index" % (LOG2_N, gpus)}
 
 
 # ------------------------------------------------------------------------------ extras (N=1)
@@ -912,13 +915,26 @@ def run_gpu(args):
             if rank == 0:
                 print("bench.py: peer-memory exchange unavailable (%s); using NCCL all_to_all" % str(e)[:200], file=sys.stderr)
             shard_call, exch = sp.knearest_fast, "nccl"
-        for _ in range(3):
-            si, sd, sst = shard_call(q_dev, K)
+        def shard_steps(nsteps):
+            """nsteps batches, every one validated before this returns.  Peer-memory exchange: the batches are
+            STREAMED -- the host reads batch i's deferred count (and would run its exact fallback) after it has
+            issued batch i + 1, so that read does not idle the GPU."""
+            if exch != "p2p":
+                for _ in range(nsteps):
+                    res = shard_call(q_dev, K)
+                return res
+            pend = None
+            for _ in range(nsteps):
+                nxt = sp.knearest_p2p_async(q_dev, K)
+                if pend is not None:
+                    pend.wait()
+                pend = nxt
+            return pend.wait()
+        si, sd, sst = shard_steps(3)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(args.steps):
-            si, sd, sst = shard_call(q_dev, K)
+        si, sd, sst = shard_steps(args.steps)
         s1.record()
         barrier()
         t = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device="cuda")

@@ -6,6 +6,8 @@
 //     region the rank covers, halo included); halo copies can be blanked for the all-ranks fallback;
 //   * unpack: records back into the caller's (idx, dist, count) arrays at the original query positions.
 // The collectives themselves are issued by the host binding through torch.distributed (NCCL over NVLink).
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace pomp;
@@ -13,6 +15,7 @@ using namespace pomp;
 namespace {
 
 constexpr int SHARD_MAX_RANKS = 64;
+constexpr int ROUTE_QPT = 8;  // queries per thread of the peer-memory routing kernel
 
 struct Bounds {
   double b[SHARD_MAX_RANKS];  // b[r] = lower bound of rank r's slab (b[0] = -inf is implied), n_ranks - 1 used
@@ -232,30 +235,71 @@ struct PeerPtrs {
 __global__ void __launch_bounds__(256)
 route_p2p_kernel(const double* __restrict__ q, long long nq, int D, int axis, Bounds B, int n_ranks, int my_rank,
                  long long cap, unsigned long long* __restrict__ cursor, PeerPtrs rq, int64_t* __restrict__ perm,
-                 int64_t* __restrict__ defer_list, unsigned long long* __restrict__ defer_count, long long defer_cap) {
-  __shared__ unsigned int sc[SHARD_MAX_RANKS];
+                 int64_t* __restrict__ defer_list, unsigned long long* __restrict__ defer_count, long long defer_cap,
+                 int qpt) {
+  // A block takes 256 * qpt queries, sorts them by destination rank in SHARED memory and then writes one contiguous
+  // run per destination: the NVLink stores are full 128-byte lines (one query per thread wrote 16-byte pieces in
+  // smem-atomic order -- 0.11 ms for 2^20 queries on 8 GPUs), and a block needs ONE global atomic per destination.
+  extern __shared__ __align__(16) unsigned char route_smem[];
+  __shared__ unsigned int sc[SHARD_MAX_RANKS], pre[SHARD_MAX_RANKS + 1];
   __shared__ unsigned long long base[SHARD_MAX_RANKS];
+  const int nQ = blockDim.x * qpt;
+  double* sq = reinterpret_cast<double*>(route_smem);                       // [nQ][D]
+  long long* si = reinterpret_cast<long long*>(sq + (size_t)nQ * D);         // [nQ] original index
+  unsigned char* sr = reinterpret_cast<unsigned char*>(si + nQ);             // [nQ] destination rank
   if (threadIdx.x < SHARD_MAX_RANKS) sc[threadIdx.x] = 0;
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int r = 0;
-  unsigned int slot = 0;
-  if (i < nq) {
-    r = owner_of(B, n_ranks, __ldg(q + i * D + axis));
-    slot = atomicAdd(&sc[r], 1u);
+  const long long i0 = (long long)blockIdx.x * nQ + threadIdx.x;
+  int r[ROUTE_QPT];
+  unsigned int slot[ROUTE_QPT];
+#pragma unroll
+  for (int u = 0; u < ROUTE_QPT; u++) {
+    const long long i = i0 + (long long)u * blockDim.x;
+    r[u] = -1;
+    slot[u] = 0;
+    if (u < qpt && i < nq) {
+      r[u] = owner_of(B, n_ranks, __ldg(q + i * D + axis));
+      slot[u] = atomicAdd(&sc[r[u]], 1u);
+    }
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int acc = 0;
+    for (int j = 0; j < n_ranks; j++) {
+      pre[j] = acc;
+      acc += sc[j];
+    }
+    pre[n_ranks] = acc;
+  }
   if (threadIdx.x < n_ranks && sc[threadIdx.x]) base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
   __syncthreads();
-  if (i < nq) {
-    const unsigned long long t = base[r] + slot;
+#pragma unroll
+  for (int u = 0; u < ROUTE_QPT; u++) {
+    if (r[u] < 0) continue;
+    const long long i = i0 + (long long)u * blockDim.x;
+    const unsigned int e = pre[r[u]] + slot[u];
+    for (int j = 0; j < D; j++) sq[(size_t)e * D + j] = __ldg(q + i * D + j);
+    si[e] = i;
+    sr[e] = (unsigned char)r[u];
+  }
+  __syncthreads();
+  const unsigned int total = pre[n_ranks];
+  // coordinates: consecutive threads write consecutive doubles of one destination's run
+  for (unsigned int w = threadIdx.x; w < total * (unsigned)D; w += blockDim.x) {
+    const unsigned int e = w / (unsigned)D, j = w - e * (unsigned)D;
+    const int rr = sr[e];
+    const unsigned long long t = base[rr] + (e - pre[rr]);
+    if (t < (unsigned long long)cap)
+      reinterpret_cast<double*>(rq.p[rr])[((long long)my_rank * cap + (long long)t) * D + j] = sq[w];  // peer store
+  }
+  for (unsigned int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int rr = sr[e];
+    const unsigned long long t = base[rr] + (e - pre[rr]);
     if (t < (unsigned long long)cap) {
-      double* dst = reinterpret_cast<double*>(rq.p[r]) + ((long long)my_rank * cap + (long long)t) * D;  // peer store
-      for (int j = 0; j < D; j++) dst[j] = __ldg(q + i * D + j);
-      perm[(long long)r * cap + (long long)t] = i;
+      perm[(long long)rr * cap + (long long)t] = si[e];
     } else {
       const unsigned long long d = atomicAdd(defer_count, 1ull);
-      if ((long long)d < defer_cap) defer_list[d] = i;
+      if ((long long)d < defer_cap) defer_list[d] = si[e];
     }
   }
 }
@@ -331,9 +375,16 @@ POMP_API int pomp_shard_route_p2p(const double* q, int64_t nq, int32_t dim, int3
     B.b[r] = (r < n_ranks - 1 && bounds_h) ? bounds_h[r] : INFINITY;
     P.p[r] = r < n_ranks ? (void*)(uintptr_t)peer_query_blocks_h[r] : nullptr;
   }
-  LAUNCH(route_p2p_kernel, (int)((nq + 255) / 256), 256, 0, (cudaStream_t)stream, q, (long long)nq, dim, axis, B, n_ranks,
-         my_rank, (long long)cap, (unsigned long long*)counters, P, perm_out, defer_list,
-         (unsigned long long*)(counters + SHARD_MAX_RANKS), (long long)defer_cap);
+  {
+    // queries per thread: as many as 48 KB of staging (D doubles + index + rank per query) allow, at most ROUTE_QPT
+    const size_t per_q = (size_t)dim * 8 + 8 + 1;
+    int qpt = (int)std::min<size_t>(ROUTE_QPT, std::max<size_t>(1, (48 * 1024 - 64) / (256 * per_q)));
+    const size_t smem = (size_t)256 * qpt * per_q + 16;
+    const long long per_block = 256LL * qpt;
+    LAUNCH(route_p2p_kernel, (int)((nq + per_block - 1) / per_block), 256, smem, (cudaStream_t)stream, q, (long long)nq, dim,
+           axis, B, n_ranks, my_rank, (long long)cap, (unsigned long long*)counters, P, perm_out, defer_list,
+           (unsigned long long*)(counters + SHARD_MAX_RANKS), (long long)defer_cap, qpt);
+  }
   CHECK_LAUNCH();
   return POMP_OK;
 }

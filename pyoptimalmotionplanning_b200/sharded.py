@@ -124,10 +124,14 @@ class _CudaShardOps(object):
 
     def local_knn(self, q, k):
         nq = q.shape[0]
+        if nq and self.pts.shape[0]:
+            # every row is written by the search (missing neighbours as -1 / inf): no fill kernels
+            idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            dst = torch.empty((nq, k), dtype=torch.float64, device=q.device)
+            self.nn.knearest_device(q.data_ptr(), nq, k, idx.data_ptr(), dst.data_ptr(), None, self._st())
+            return idx, dst
         idx = torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
         dst = torch.full((nq, k), float("inf"), dtype=torch.float64, device=q.device)
-        if nq and self.pts.shape[0]:
-            self.nn.knearest_device(q.data_ptr(), nq, k, idx.data_ptr(), dst.data_ptr(), None, self._st())
         return idx, dst
 
     def local_neighbors(self, q, radius, inclusive):
@@ -172,6 +176,25 @@ class _CudaShardOps(object):
         idx_in = rec_g[..., 1].contiguous()
         dist_in = rec_g[..., 0].contiguous().view(torch.float64)
         return _cuda_merge(idx_in, dist_in, k)
+
+
+class _PendingKnn(object):
+    """A sharded k-NN batch whose kernels are in flight (SpatialShardedNearestNeighbors.knearest_p2p_async)."""
+
+    def __init__(self, owner, q, k, idx, dst, dlist, dcount, pin, event, cap, fallback_slots, mark):
+        self.owner, self.q, self.k, self.idx, self.dst = owner, q, k, idx, dst
+        self.dlist, self.dcount, self.pin, self.event = dlist, dcount, pin, event
+        self.cap, self.fallback_slots, self._mark = cap, fallback_slots, mark
+
+    def wait(self):
+        """Collective (same order on every rank).  (idx[nq,k] global int64, dist[nq,k], stats)."""
+        self.event.synchronize()
+        n_def, n_worst = int(self.pin[0]), int(self.pin[1])
+        self._mark("host read")
+        if n_worst > 0:
+            self.owner._fallback(self.q, self.k, self.dlist, self.dcount, n_worst, self.fallback_slots, self.idx, self.dst)
+            self._mark("fallback")
+        return self.idx, self.dst, {"deferred": n_def, "deferred_worst_rank": n_worst, "block_slots": self.cap}
 
 
 class SpatialShardedNearestNeighbors(object):
@@ -405,14 +428,25 @@ class SpatialShardedNearestNeighbors(object):
         worst = dcount.clone()
         if G > 1:
             dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
-        n_def, n_worst = torch.cat([dcount, worst]).tolist()
-        mark("sync")
+        mark("deferred-count all_reduce")
+        n_def, n_worst = self._read_counts(dcount, worst)
+        mark("host read")
         if n_worst > 0:
             self._fallback(q, k, dlist, dcount, n_worst, fallback_slots, idx, dst)
             mark("fallback")
         return idx, dst, {"deferred": n_def, "deferred_worst_rank": n_worst, "block_slots": cap}
 
     # ------------------------------------------------------------------ peer-memory exchange (NVLink stores, no NCCL)
+    def _read_counts(self, dcount, worst):
+        """(own deferred, worst rank's deferred) on the host: two 8-byte copies into pinned memory and one stream
+        synchronisation (torch.cat + tolist costs a kernel and a pageable copy more)."""
+        if getattr(self, "_pin2", None) is None:
+            self._pin2 = torch.empty(2, dtype=torch.int64).pin_memory()
+        self._pin2[0:1].copy_(dcount, non_blocking=True)
+        self._pin2[1:2].copy_(worst, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(self._pin2[0]), int(self._pin2[1])
+
     def _p2p_setup(self, cap, k, dev):
         import torch.distributed._symmetric_memory as symm
         key = (cap, k)
@@ -439,6 +473,15 @@ class SpatialShardedNearestNeighbors(object):
         the peers' receive buffers (torch symmetric memory supplies the mapped peer pointers and the device barrier):
         route+send is ONE kernel, finalize+return is ONE kernel, two barriers per step, no NCCL call on the data
         path (one tiny all_reduce tells whether any query was deferred).  Same answers."""
+        return self.knearest_p2p_async(q, k, slack, fallback_slots, _trace).wait()
+
+    def knearest_p2p_async(self, q, k, slack=1.04, fallback_slots=4096, _trace=None):
+        """The same exchange, issued without the host synchronisation at its end.  Returns a pending result whose
+        wait() reads the deferred count of THIS batch (a CUDA event recorded behind its two 8-byte copies, not a
+        device synchronisation), runs the exact fallback if anything was deferred and hands back (idx, dist, stats).
+        A caller that streams batches calls wait() of batch i after issuing batch i + 1: the host read no longer
+        idles the GPU.  Collective: every rank issues and waits in the same order; `q` must stay unchanged until
+        wait() returns (the fallback re-reads the deferred queries from it)."""
         ops, G, ax, D = self.ops, self.world, self.axis, self.dim
         C, lib, check, st = ops.C, ops.lib, ops._abi.check, ops._st()
 
@@ -461,16 +504,18 @@ class SpatialShardedNearestNeighbors(object):
         check(lib, lib.pomp_shard_route_p2p(C.c_void_p(q.data_ptr()), nq, D, ax, b, G, self.rank, cap,
                                             C.c_void_p(ctr.data_ptr()), self._rq_ptrs, C.c_void_p(self._perm.data_ptr()),
                                             C.c_void_p(dlist.data_ptr()), nq, C.c_void_p(st)))
+        mark("route+send kernel")
         self._rq_h.barrier(channel=0)
-        mark("route+send")
+        mark("barrier")
         recvq = self._rq.view(n_slots, D)
         il, dl = ops.local_knn(recvq, k)
         mark("local_search")
         check(lib, lib.pomp_shard_finalize_p2p(C.c_void_p(recvq.data_ptr()), cap, G, self.rank, D, ax, float(self.lo_cov),
                                                float(self.hi_cov), k, C.c_void_p(il.data_ptr()), C.c_void_p(dl.data_ptr()),
                                                C.c_void_p(self.l2g.data_ptr()), self._rb_ptrs, C.c_void_p(st)))
+        mark("finalize+return kernel")
         self._rb_h.barrier(channel=1)
-        mark("finalize+return")
+        mark("barrier")
         idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         dst = torch.empty((nq, k), dtype=torch.float64, device=dev)
         dcount = ctr[64:65]
@@ -481,12 +526,19 @@ class SpatialShardedNearestNeighbors(object):
         worst = dcount.clone()
         if G > 1:
             dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
-        n_def, n_worst = torch.cat([dcount, worst]).tolist()
-        mark("sync")
-        if n_worst > 0:
-            self._fallback(q, k, dlist, dcount, n_worst, fallback_slots, idx, dst)
-            mark("fallback")
-        return idx, dst, {"deferred": n_def, "deferred_worst_rank": n_worst, "block_slots": cap}
+        mark("deferred-count all_reduce")
+        # (own, worst rank's) deferred counts into one of a few rotating pinned buffers, an event behind the copies
+        pool = getattr(self, "_pin_pool", None)
+        if pool is None:
+            pool = self._pin_pool = [torch.empty(2, dtype=torch.int64).pin_memory() for _ in range(8)]
+            self._pin_next = 0
+        pin = pool[self._pin_next]
+        self._pin_next = (self._pin_next + 1) % len(pool)
+        pin[0:1].copy_(dcount, non_blocking=True)
+        pin[1:2].copy_(worst, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return _PendingKnn(self, q, k, idx, dst, dlist, dcount, pin, ev, cap, fallback_slots, mark)
 
     def _fallback(self, q, k, dlist, dcount, n_worst, fallback_slots, idx, dst):
         """Exact answers for the deferred queries: a block of F slots per rank (the same F everywhere), answered by
