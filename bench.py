@@ -710,6 +710,34 @@ def run_striped(world, rank, local, barrier):
     dn = torch.tensor([sum(rf.totalIters) - done0], dtype=torch.float64, device="cuda")
     dist.all_reduce(dn, op=dist.ReduceOp.SUM)
     out["rrrt_bugtrap_lockstep_trials"] = {"iters_per_s": float(dn.item()) / float(dt.item()), "global_trials": T}
+    # BASELINE config 5: 4096 seeded DoubleIntegrator sst* trials striped over the GPUs (512 per GPU on 8), lock-step
+    # on each GPU (csrc/sst.cu); needs the staged reference copy for the problem definition (oracle/_ref)
+    try:
+        import contextlib
+        import io
+        from oracle import refshim
+        if refshim.available():
+            refshim.load()
+            from pomp.example_problems import doubleintegrator
+            from pyoptimalmotionplanning_b200.sst import SSTStarForest
+            TS = 4096
+            s0i, s1i = stripe(TS, rank, world)
+            prob = doubleintegrator.doubleIntegratorTest()
+            with contextlib.redirect_stdout(io.StringIO()):
+                f = SSTStarForest(prob.controlSpace, prob.start, prob.goal, list(range(s0i, s1i)), prob.objective,
+                                  selectionRadius=0.3, witnessRadius=0.3, device=local)
+                f.planMore(20)
+                barrier()
+                tw = time.perf_counter()
+                its = 100
+                f.planMore(its)
+                torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device="cuda")
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            out["sststar_doubleintegrator_lockstep_trials"] = {"iters_per_s": TS * its / float(dt.item()),
+                                                               "global_trials": TS, "iters_per_trial": its}
+    except Exception as e:   # an extra: never takes the bench down
+        out["sststar_doubleintegrator_lockstep_trials"] = {"error": repr(e)[:200]}
     return out
 
 
