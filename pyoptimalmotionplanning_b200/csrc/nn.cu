@@ -846,7 +846,12 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   // (k = 16 prefers 2.0: 1.17 vs 1.44 ms -- set the points_per_cell knob for k-NN-heavy callers)
   // generic metrics (SE(2) states, 2^24 points): 3.1 ms at 2, 2.8 ms at 4 points per cell (profiles/se2_probe.py)
   const bool generic3 = G == 3 && !is_plain_euclid(h->metric);
-  double ppc = h->points_per_cell > 0 ? h->points_per_cell : (G == 2 ? 1.5 : (G == 3 ? (generic3 ? 4.0 : 2.0) : 4.0));  // 4-D / 6-D: 4 beats 2, 8, 16 (bench extras)
+  // 4-D: 4 beats 2, 8, 16 for both kernel families.  6-D Euclidean (warp-per-query shell kernel, whose cost is the row
+  // enumeration): 8 beats 4 -- k = 1 / 4 / 8 / 16: 6.9 / 10.8 / 14.2 / 19.4 ms vs 7.1 / 11.7 / 15.7 / 21.7 ms
+  // (profiles/ppc6_probe.py); the thread-per-query kernels preferred 4 there (k = 8: 14.9 vs 20.3 ms at 8)
+  const bool warp6 = G >= 6 && is_plain_euclid(h->metric) && h->warp_search != 0;
+  double ppc = h->points_per_cell > 0 ? h->points_per_cell
+                                      : (G == 2 ? 1.5 : (G == 3 ? (generic3 ? 4.0 : 2.0) : (warp6 ? 8.0 : 4.0)));
   double target = fmax(1.0, (double)n / ppc);
   target = fmin(target, 268435456.0);
   // cubic cells in metric space: ncell_a proportional to the weighted extent

@@ -26,10 +26,11 @@ bool pomp::warp_knn_eligible(const pomp_nn* h, int k) {
   // measured on B200 (2^20 queries vs 2^24 points, thread-per-query -> this kernel; profiles/knn_sweep.py):
   //   3-D  k = 4: 1.00 -> 1.41 ms   k = 8: 1.44 -> 1.80 ms   k = 16: 4.61 -> 2.27 ms (16 lanes per query)
   //   4-D  k = 4: 2.01 -> 2.60 ms   k = 8: 2.97 -> 3.05 ms   k = 16: 7.68 -> 4.04 ms
-  //   6-D  k = 1: 9.2 -> 7.2 ms   k = 4: 23.3 -> 11.8 ms   k = 8: 15.0 -> 15.7 ms   k = 16: 29.2 -> 21.8 ms
+  //   6-D  k = 1: 9.2 -> 7.2 ms   k = 4: 23.3 -> 11.8 ms   k = 8: 15.0 -> 15.7 ms   k = 16: 29.2 -> 21.8 ms (4 points
+  //        per cell; 6.9 / 10.8 / 14.2 / 19.4 ms at the 8 the index now uses in 6-D)
   //   2-D  k = 4 / 8 / 16: 0.32 / 0.54 / 1.20 -> 0.68 / 0.79 / 1.18 ms: the thread kernels keep 2-D
   if (h->D == 2) return false;
-  if (h->D == 6) return k <= 4 || k > 8;
+  if (h->D == 6) return true;  // with the 8 points per cell the index is built with there (k = 8: 14.2 vs 20.3 ms)
   return k > 8;
 }
 
