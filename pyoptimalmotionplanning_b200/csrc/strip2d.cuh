@@ -12,7 +12,7 @@
 //   * inside a strip the rows follow each other, so a TILE (ST_TW x ST_TH cells) together with its full
 //     one-cell halo -- rows y0-1 .. y0+ST_TH of the strip -- is ONE contiguous run of points: one bulk copy;
 //   * per tile, the offsets of its (ST_TH+2) x (ST_TW+2) local cells inside that run, as uint16
-//     (tile-local: one more bulk copy, 2.4 KB);
+//     (tile-local: one more bulk copy, 4.5 KB);
 //   * sidx2[slot] = insertion index of every (replicated) slot.
 // Queries are bucketed by tile in ONE pass (fixed-capacity buckets, one padded counter per tile: no scan, no
 // second pass); tile ids are strip-major, so consecutive tiles share halo rows in L2.
@@ -37,16 +37,29 @@
 
 namespace pomp {
 
+// Tile geometry, measured on B200 (2^20 queries vs 2^24 points, ms per step; tile height / consumer warps per group /
+// stage buffers): 16/4/6 0.1126 (the first tuned version), 16/3/6 0.1149, 16/5/6 0.1104, 8/2/12 0.1258, 24/6/4
+// 0.1104, 24/7/4 0.1094, 32/8/3 0.1096, 48/12/2 0.1128, 32/10/3 0.1079: taller tiles replicate fewer halo rows
+// (34/32 instead of 18/16) and 31 consumer warps (64 registers each) hide more of the per-query latency.
+#ifndef POMP_ST_TH
+#define POMP_ST_TH 32
+#endif
+#ifndef POMP_ST_WG
+#define POMP_ST_WG 10
+#endif
+#ifndef POMP_ST_STAGES
+#define POMP_ST_STAGES 3
+#endif
 constexpr int ST_TW = 64;   // tile width in cells (= strip width)
-constexpr int ST_TH = 16;   // tile height in cells
+constexpr int ST_TH = POMP_ST_TH;   // tile height in cells
 constexpr int ST_LW = ST_TW + 2;  // local cell row incl. halo
 constexpr int ST_LH = ST_TH + 2;
-constexpr int ST_NCELL = ST_LW * ST_LH;            // 1188 local cells
-constexpr int ST_CS_STRIDE = (ST_NCELL + 1 + 7) / 8 * 8;  // uint16 entries per tile, 16-byte multiple (1192)
+constexpr int ST_NCELL = ST_LW * ST_LH;            // 2244 local cells (66 x 34)
+constexpr int ST_CS_STRIDE = (ST_NCELL + 1 + 7) / 8 * 8;  // uint16 entries per tile, 16-byte multiple (2248 for 64 x 32 cells)
 constexpr int ST_CS_BYTES = ST_CS_STRIDE * 2;
 constexpr int ST_OLIST = 1024;   // CTA-local deferred list (expected ~20 entries per CTA at the bench density)
-constexpr int ST_WG = 4;         // consumer warps per group (one stage buffer per group): 128 queries per sweep
-constexpr int ST_MAX_STAGES = 6; // groups = stage buffers; how many fit is decided at launch from the cell occupancy
+constexpr int ST_WG = POMP_ST_WG; // consumer warps per group (one stage buffer per group): 320 queries per sweep
+constexpr int ST_MAX_STAGES = POMP_ST_STAGES; // groups = stage buffers; how many fit is decided at launch from the cell occupancy
 constexpr int ST_THREADS = (ST_MAX_STAGES * ST_WG + 1) * 32;
 constexpr int ST_HDR_BYTES = 96;   // stage header: tile, first slot, next tile, sub-bucket prefix sums of both
 constexpr int ST_SUB = 8;          // sub-buckets per tile: same-address atomics serialise at ~0.25 us each in L2
