@@ -62,7 +62,10 @@ constexpr int ST_WG = POMP_ST_WG; // consumer warps per group (one stage buffer 
 constexpr int ST_MAX_STAGES = POMP_ST_STAGES; // groups = stage buffers; how many fit is decided at launch from the cell occupancy
 constexpr int ST_THREADS = (ST_MAX_STAGES * ST_WG + 1) * 32;
 constexpr int ST_HDR_BYTES = 96;   // stage header: tile, first slot, next tile, sub-bucket prefix sums of both
-constexpr int ST_SUB = 8;          // sub-buckets per tile: same-address atomics serialise at ~0.25 us each in L2
+#ifndef POMP_ST_SUB
+#define POMP_ST_SUB 8
+#endif
+constexpr int ST_SUB = POMP_ST_SUB;          // sub-buckets per tile: same-address atomics serialise at ~0.25 us each in L2
                                    // (95 queries on one counter: 23 us for the bucketing pass; 12 per counter: hidden)
 constexpr int ST_CNT_STRIDE = 8;   // ints between two counters: one counter per 32-byte sector
 
