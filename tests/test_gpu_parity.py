@@ -799,6 +799,29 @@ def test_spatial_shard_kernels_match_numpy_ops():
     fi, fd, fst = sp.knearest_fast(torch.from_numpy(bq).cuda(), 4, slack=0.5)   # blocks too small: the rest is deferred
     assert (fi.cpu().numpy() == oi).all() and (fd.cpu().numpy() == od).all() and fst["deferred"] > 10000
     sp.hi_cov = float("inf")
+    # peer-memory exchange (NVLink stores from the routing / finalize kernels; one rank: its own buffers), synchronous
+    # and streamed (wait() of batch i after batch i + 1 was issued), with and without deferred queries
+    try:
+        sp.knearest_p2p(torch.from_numpy(bq).cuda(), 4)
+        p2p = True
+    except Exception as e:      # no symmetric memory on this box
+        print("peer-memory exchange unavailable:", str(e)[:200])
+        p2p = False
+    if p2p:
+        qd = torch.from_numpy(bq).cuda()
+        qd2 = torch.from_numpy(bq[::-1].copy()).cuda()
+        pi_, pd_, pst = sp.knearest_p2p(qd, 4)
+        assert (pi_.cpu().numpy() == oi).all() and (pd_.cpu().numpy() == od).all() and pst["deferred"] == 0
+        pend = [sp.knearest_p2p_async(qd, 4), sp.knearest_p2p_async(qd2, 4)]
+        sp.hi_cov = 0.97                                  # the third batch loses certificates -> fallback in wait()
+        pend.append(sp.knearest_p2p_async(qd, 4))
+        sp.hi_cov = float("inf")
+        pend.append(sp.knearest_p2p_async(qd, 4, slack=0.5))   # blocks too small -> deferred at routing time
+        res = [p_.wait() for p_ in pend]
+        for j, (ri, rd, rst) in enumerate(res):
+            want_i, want_d = (oi[::-1], od[::-1]) if j == 1 else (oi, od)
+            assert (ri.cpu().numpy() == want_i).all() and (rd.cpu().numpy() == want_d).all(), j
+        assert res[0][2]["deferred"] == 0 and res[2][2]["deferred"] > 500 and res[3][2]["deferred"] > 10000
     off, hits = sp.neighbors(torch.from_numpy(bq[:2000]).cuda(), 0.004)
     ooff, ohits = oracle.nn_neighbors(m, big, bq[:2000], 0.004, True)
     assert (off.cpu().numpy() == ooff).all() and (hits.cpu().numpy() == ohits).all()
