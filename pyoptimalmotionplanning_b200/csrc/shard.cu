@@ -316,11 +316,13 @@ finalize_p2p_kernel(const double* __restrict__ q, long long n_slots, long long c
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
   const long long src = i / cap, t = i - src * cap;
-  // word-major block [2k+1][n_ranks*cap]: consecutive lanes store consecutive 8-byte words (coalesced NVLink stores)
+  // word-major block [2k][n_ranks*cap]: consecutive lanes store consecutive 8-byte words (coalesced NVLink stores)
   int64_t* row = reinterpret_cast<int64_t*>(rb.p[src]) + ((long long)my_rank * cap + t);
   const long long ws = n_slots;
   double kth = POMP_INF;
   bool full = true;
+  double d0 = POMP_INF;
+  int64_t g0 = -1;
   for (int j = 0; j < k; j++) {
     const int64_t li = idx_local[i * k + j];
     double d = dist[i * k + j];
@@ -331,15 +333,23 @@ finalize_p2p_kernel(const double* __restrict__ q, long long n_slots, long long c
     } else {
       kth = d;
     }
-    row[(2 * j) * ws] = __double_as_longlong(d);
-    row[(2 * j + 1) * ws] = gi;
+    if (j > 0) {  // entry 0 is stored last: its index word carries the certificate
+      row[(2 * j) * ws] = __double_as_longlong(d);
+      row[(2 * j + 1) * ws] = gi;
+    } else {
+      d0 = d;
+      g0 = gi;
+    }
   }
   const double y = q[i * D + axis];
   const double margin = fmin(y - lo_cov, hi_cov - y);
-  row[(2 * k) * ws] = (full && kth < margin) ? 0 : 1;
+  // no certificate (the k-th distance reaches beyond the region this rank covers, or fewer than k points): the index
+  // word of entry 0 says so (-2; a missing neighbour is -1) -- two words per neighbour over NVLink instead of 2k + 1
+  row[0] = __double_as_longlong(d0);
+  row[ws] = (full && kth < margin) ? g0 : -2;
 }
 
-// result block [2k+1][n_ranks][cap] (word-major) -> the caller's arrays; slot (r, t) is valid for t < min(cursor[r], cap)
+// result block [2k][n_ranks][cap] (word-major; allocated with 2k+1 rows) -> the caller's arrays; slot (r, t) is valid for t < min(cursor[r], cap)
 __global__ void __launch_bounds__(256)
 unpack_p2p_kernel(const int64_t* __restrict__ rows, int n_ranks, long long cap, int k, const int64_t* __restrict__ perm,
                   const unsigned long long* __restrict__ cursor, int64_t* __restrict__ out_idx,
@@ -352,7 +362,7 @@ unpack_p2p_kernel(const int64_t* __restrict__ rows, int n_ranks, long long cap, 
   const long long o = perm[i];
   const long long ws = (long long)n_ranks * cap;
   const int64_t* row = rows + i;
-  if (row[(2 * k) * ws]) {
+  if (row[ws] == -2) {  // the owner could not certify this query (finalize_p2p_kernel)
     const unsigned long long d = atomicAdd(defer_count, 1ull);
     if ((long long)d < defer_cap) defer_list[d] = o;
     return;
