@@ -154,7 +154,10 @@ __device__ __forceinline__ void strip_store_rec(StripQRec* dst, double x, double
   asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "l"(qi), "l"(0LL) : "memory");
 }
 
-constexpr int ST_QPT = 4;  // queries per thread: independent load -> atomic -> store chains in flight
+#ifndef POMP_ST_QPT
+#define POMP_ST_QPT 4
+#endif
+constexpr int ST_QPT = POMP_ST_QPT;  // queries per thread: independent load -> atomic -> store chains in flight
 static __global__ void __launch_bounds__(256)
 strip_qbucket_kernel(GridDev g, int nty, const double2* __restrict__ q, long long nq, int Cs, int* __restrict__ ctrl,
                      StripQRec* __restrict__ qrec, int* __restrict__ ovf_list) {
