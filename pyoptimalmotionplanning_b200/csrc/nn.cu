@@ -1075,12 +1075,7 @@ static int grid_knn_search(pomp_nn* h, const SortInfo& si, const double* q, int6
                            double* dist, int32_t* cnt, cudaStream_t st) {
   const int* qperm = si.qperm;
   const double* qsorted = si.qsorted;
-  const int* qstart = si.qstart;
-  const int shift = si.shift, nbx = si.nbx;
   const bool fast = knn_is_fast(h, k);
-  (void)qstart;
-  (void)shift;
-  (void)nbx;
   if (fast && warp_knn_eligible(h, k)) return launch_grid_knn_warp(h, q, qsorted, nq, qperm, k, idx, dist, cnt, st);
   if (fast) {
     switch (h->D) {

@@ -127,7 +127,7 @@ sst_step_kernel(SstDev d, SpaceDev s, pomp_dyn_desc dy, pomp_metric_desc geo, in
   __shared__ int si[SST_THREADS / 32];
   __shared__ double path[SST_MAXWP][POMP_MAX_DIM];
   __shared__ double s_xrand[POMP_MAX_DIM], s_u[POMP_MAX_DIM];
-  __shared__ int s_np, s_go, s_better;
+  __shared__ int s_np, s_go;
   __shared__ long long s_k;
   if (restart_now) {
     if (tid == 0) sst_reset_trial(d, t);
@@ -295,7 +295,6 @@ sst_step_kernel(SstDev d, SpaceDev s, pomp_dyn_desc dy, pomp_metric_desc geo, in
         }
         if (goal.r >= 0.0 && metric_eval(geo, xnew, goal.c) <= goal.r && newcost < d.best[t]) d.best[t] = newcost;
       }
-      s_better = go;
     }
     __syncthreads();
   }
