@@ -428,25 +428,41 @@ __global__ void bf_radius_kernel(const double* __restrict__ pts, long long n, po
 }
 
 // ============================================================================ grid build kernels
-__global__ void bbox_kernel(const double* __restrict__ pts, long long n, int D, double* __restrict__ part) {
-  double mn[POMP_MAX_DIM], mx[POMP_MAX_DIM];
-  for (int j = 0; j < D; j++) {
+// DC > 0: compile-time dimension (bounds in registers, compare + select: sm_100 has no FP64 min / max instruction and
+// fmin / fmax expand to a NaN-aware sequence; `v < mn ? v : mn` ignores NaN coordinates the same way); DC = 0: any D
+template <int DC>
+__global__ void __launch_bounds__(256)
+bbox_kernel(const double* __restrict__ pts, long long n, int D, double* __restrict__ part) {
+  constexpr int DA = DC ? DC : POMP_MAX_DIM;
+  const int dim = DC ? DC : D;
+  double mn[DA], mx[DA];
+#pragma unroll
+  for (int j = 0; j < DA; j++) {
     mn[j] = POMP_INF;
     mx[j] = -POMP_INF;
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    for (int j = 0; j < D; j++) {
-      double v = pts[i * D + j];
-      mn[j] = fmin(mn[j], v);
-      mx[j] = fmax(mx[j], v);
-    }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double p[DA];
+    if (DC) load_point<DA>(pts, i, p);
+    else
+      for (int j = 0; j < dim; j++) p[j] = pts[i * dim + j];
+#pragma unroll
+    for (int j = 0; j < DA; j++)
+      if (j < dim) {
+        mn[j] = p[j] < mn[j] ? p[j] : mn[j];
+        mx[j] = p[j] > mx[j] ? p[j] : mx[j];
+      }
+  }
   __shared__ double smn[32][POMP_MAX_DIM], smx[32][POMP_MAX_DIM];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = 0; j < D; j++) {
+#pragma unroll
+  for (int j = 0; j < DA; j++) {
+    if (j >= dim) break;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      mn[j] = fmin(mn[j], __shfl_xor_sync(FULL_MASK, mn[j], o));
-      mx[j] = fmax(mx[j], __shfl_xor_sync(FULL_MASK, mx[j], o));
+      const double a = __shfl_xor_sync(FULL_MASK, mn[j], o), b2 = __shfl_xor_sync(FULL_MASK, mx[j], o);
+      mn[j] = a < mn[j] ? a : mn[j];
+      mx[j] = b2 > mx[j] ? b2 : mx[j];
     }
     if (lane == 0) {
       smn[w][j] = mn[j];
@@ -454,12 +470,12 @@ __global__ void bbox_kernel(const double* __restrict__ pts, long long n, int D, 
     }
   }
   __syncthreads();
-  if (threadIdx.x < D) {
+  if (threadIdx.x < dim) {
     int j = threadIdx.x;
     double a = POMP_INF, b = -POMP_INF;
     for (int x = 0; x < nw; x++) {
-      a = fmin(a, smn[x][j]);
-      b = fmax(b, smx[x][j]);
+      a = smn[x][j] < a ? smn[x][j] : a;
+      b = smx[x][j] > b ? smx[x][j] : b;
     }
     part[((long long)blockIdx.x * 2 + 0) * POMP_MAX_DIM + j] = a;
     part[((long long)blockIdx.x * 2 + 1) * POMP_MAX_DIM + j] = b;
@@ -787,7 +803,11 @@ static int build_grid(pomp_nn* h, cudaStream_t st) {
   // bounding box
   int nb = std::min<int64_t>((n + 255) / 256, (int64_t)sm_count(h->device) * 8);
   POMP_TRY(h->part_d.reserve((size_t)nb * 2 * POMP_MAX_DIM));
-  LAUNCH(bbox_kernel, nb, 256, 0, st, h->d_pts, (long long)n, D, h->part_d.p);
+  if (D == 2) LAUNCH(bbox_kernel<2>, nb, 256, 0, st, h->d_pts, (long long)n, D, h->part_d.p);
+  else if (D == 3) LAUNCH(bbox_kernel<3>, nb, 256, 0, st, h->d_pts, (long long)n, D, h->part_d.p);
+  else if (D == 4) LAUNCH(bbox_kernel<4>, nb, 256, 0, st, h->d_pts, (long long)n, D, h->part_d.p);
+  else if (D == 6) LAUNCH(bbox_kernel<6>, nb, 256, 0, st, h->d_pts, (long long)n, D, h->part_d.p);
+  else LAUNCH(bbox_kernel<0>, nb, 256, 0, st, h->d_pts, (long long)n, D, h->part_d.p);
   CHECK_LAUNCH();
   std::vector<double> part((size_t)nb * 2 * POMP_MAX_DIM);
   CUDA_TRY(cudaMemcpyAsync(part.data(), h->part_d.p, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st));
