@@ -883,6 +883,7 @@ struct RadiusStage {
   int inclusive;
   int cnt;
   int* stage;  // this query's RADIUS_STAGE_CAP slots
+  IdxResolver res;
   __device__ __forceinline__ double threshold() const { return radius; }
   __device__ __forceinline__ double tsq_up() const { return tsq; }
   __device__ __forceinline__ void offer_sq(double s, int pos) {
@@ -890,22 +891,28 @@ struct RadiusStage {
     double d = sqrt(s);
     bool hit = inclusive ? (d <= radius) : (d < radius);
     if (hit) {
-      if (cnt < RADIUS_STAGE_CAP) stage[cnt] = pos;
+      // parked as the INSERTION index: its gather overlaps the traversal's other loads here, in the finalize
+      // kernel it was a dependent round trip per query
+      if (cnt < RADIUS_STAGE_CAP) stage[cnt] = res(pos);
       cnt++;
     }
   }
 };
 
+// thread t answers query qperm[t] (bucket-sorted batches: neighbouring threads walk neighbouring cells) or t
 template <int D>
 __global__ void __launch_bounds__(128)
 grid_radius_stage_kernel(GridDev g, const double* __restrict__ pts, long long n, const uint8_t* __restrict__ skip,
-                         const double* __restrict__ q, long long nq, double radius, int inclusive,
+                         const double* __restrict__ q, const double* __restrict__ qsorted,
+                         const int* __restrict__ qperm, long long nq, double radius, int inclusive,
                          int* __restrict__ counts, int* __restrict__ stage, int* __restrict__ n_long) {
-  long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (qi >= nq) return;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  const long long qi = qperm ? (long long)__ldg(qperm + t) : t;
   double qq[D];
-  load_point<D>(q, qi, qq);
-  RadiusStage c{radius, tsq_of(radius), inclusive, 0, stage + qi * RADIUS_STAGE_CAP};
+  if (qsorted) load_point<D>(qsorted, t, qq);
+  else load_point<D>(q, qi, qq);
+  RadiusStage c{radius, tsq_of(radius), inclusive, 0, stage + qi * RADIUS_STAGE_CAP, IdxResolver{g.sidx, g.n_indexed}};
   double gap[D];
 #pragma unroll
   for (int i = 0; i < D; i++) gap[i] = 0.0;
@@ -915,25 +922,26 @@ grid_radius_stage_kernel(GridDev g, const double* __restrict__ pts, long long n,
   if (c.cnt > RADIUS_STAGE_CAP) atomicAdd(n_long, 1);
 }
 
+// one warp per query: the parked insertion indices (32-bit) through a shuffle bitonic network, coalesced store
 static __global__ void __launch_bounds__(256)
 radius_finalize_kernel(const int* __restrict__ counts, const int64_t* __restrict__ offsets,
-                       const int* __restrict__ stage, IdxResolver res, long long nq, int64_t* __restrict__ out) {
+                       const int* __restrict__ stage, long long nq, int64_t* __restrict__ out) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nq) return;
   const int len = counts[w];
   if (len == 0 || len > RADIUS_STAGE_CAP) return;
-  long long v = lane < len ? (long long)res(stage[w * RADIUS_STAGE_CAP + lane]) : 0x7fffffffffffffffLL;
+  int v = lane < len ? stage[w * RADIUS_STAGE_CAP + lane] : 0x7fffffff;
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      const long long o = __shfl_xor_sync(0xffffffffu, v, j);
+      const int o = __shfl_xor_sync(0xffffffffu, v, j);
       const bool up = (lane & k) == 0, lower = (lane & j) == 0;
-      v = (lower == up) ? (v < o ? v : o) : (v > o ? v : o);
+      v = (lower == up) ? min(v, o) : max(v, o);
     }
   }
-  if (lane < len) out[offsets[w] + lane] = v;
+  if (lane < len) out[offsets[w] + lane] = (int64_t)v;
 }
 
 template <int D, bool FILL>

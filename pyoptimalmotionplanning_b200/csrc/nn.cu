@@ -1335,9 +1335,14 @@ static int radius_device(pomp_nn* h, const double* q, int64_t nq, double radius,
     int* n_long = h->counts.p + nq + 1;
     CUDA_TRY(cudaMemsetAsync(n_long, 0, sizeof(int), st));
     const int sb = (int)((nq + 127) / 128);
+    // large batches are bucket-sorted by coarse home bin first (the same sort as the k-NN path): neighbouring threads
+    // then walk neighbouring cells
+    SortInfo rsi;
+    h->cur = 0;
+    POMP_TRY(grid_knn_sort(h, h->ss[0], q, nq, 1, &rsi, st));
 #define RS(DD)                                                                                                       \
-  LAUNCH((grid_radius_stage_kernel<DD>), sb, 128, 0, st, h->grid, h->d_pts, (long long)n, skip, q, (long long)nq, radius, \
-         inclusive, h->counts.p, h->rstage.p, n_long)
+  LAUNCH((grid_radius_stage_kernel<DD>), sb, 128, 0, st, h->grid, h->d_pts, (long long)n, skip, q, rsi.qsorted,      \
+         rsi.qperm, (long long)nq, radius, inclusive, h->counts.p, h->rstage.p, n_long)
     if (h->D == 2) RS(2);
     else if (h->D == 3) RS(3);
     else if (h->D == 4) RS(4);
@@ -1355,7 +1360,7 @@ static int radius_device(pomp_nn* h, const double* q, int64_t nq, double radius,
     }
     if (total > 0) {
       LAUNCH(radius_finalize_kernel, (int)((nq * 32 + 255) / 256), 256, 0, st, h->counts.p, offsets, h->rstage.p,
-             IdxResolver{h->grid.sidx, h->grid.n_indexed}, (long long)nq, idx);
+             (long long)nq, idx);
       if (nl > 0) POMP_TRY(grid_radius(h, true, q, nq, radius, inclusive, h->counts.p, offsets, idx, st));
       CHECK_LAUNCH();
     }
