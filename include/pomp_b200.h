@@ -204,7 +204,14 @@ int pomp_shard_route_p2p(const double* q, int64_t nq, int32_t dim, int32_t axis,
                          int64_t* perm_out, int64_t* defer_list, int64_t defer_cap, void* stream);
 int pomp_shard_finalize_p2p(const double* q, int64_t cap, int32_t n_ranks, int32_t my_rank, int32_t dim, int32_t axis,
                             double lo_cov, double hi_cov, int32_t k, const int64_t* idx_local, const double* dist,
-                            const int64_t* local_to_global, const uint64_t* peer_result_blocks_h, void* stream);
+                            const int64_t* local_to_global, const uint64_t* peer_result_blocks_h,
+                            uint64_t* fails_per_asker /* device [n_ranks], may be NULL */, void* stream);
+/* the deferred counts without a collective: every rank stores its counts (route overflow of its own queries; per
+   asking rank, the queries it could not certify) into the same words of EVERY peer's flag block before the second
+   barrier of the step; afterwards pomp_shard_worst_count reduces flags[rows][cols] to the largest column sum */
+int pomp_shard_share_counts_p2p(const uint64_t* vals, int32_t ncols, const uint64_t* peer_flag_blocks_h,
+                                int64_t dst_offset, int32_t n_ranks, void* stream);
+int pomp_shard_worst_count(const int64_t* flags, int32_t rows, int32_t cols, int64_t* worst, void* stream);
 int pomp_shard_unpack_p2p(const int64_t* rows, int32_t n_ranks, int64_t cap, int32_t k, const int64_t* perm,
                           const uint64_t* counters, int64_t* idx, double* dist, int64_t* defer_list, int64_t defer_cap,
                           void* stream);

@@ -94,7 +94,9 @@ SIGNATURES = {
     "pomp_shard_finalize_rows": (C.c_int, [_P, _I64, _I32, _I32, _D, _D, _I32, _P, _P, _P, _P, _I32, _P, _P]),
     "pomp_shard_unpack_rows": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "pomp_shard_route_p2p": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I32, _I64, _P, _P, _P, _P, _I64, _P]),
-    "pomp_shard_finalize_p2p": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _D, _D, _I32, _P, _P, _P, _P, _P]),
+    "pomp_shard_finalize_p2p": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _D, _D, _I32, _P, _P, _P, _P, _P, _P]),
+    "pomp_shard_share_counts_p2p": (C.c_int, [_P, _I32, _P, _I64, _I32, _P]),
+    "pomp_shard_worst_count": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "pomp_shard_unpack_p2p": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "pomp_shard_gather_deferred": (C.c_int, [_P, _I32, _P, _P, _I64, _P, _P, _P]),
     "pomp_shard_scatter_deferred": (C.c_int, [_P, _P, _I32, _P, _P, _I64, _P, _P, _P]),

@@ -312,7 +312,8 @@ route_p2p_kernel(const double* __restrict__ q, long long nq, int D, int axis, Bo
 __global__ void __launch_bounds__(256)
 finalize_p2p_kernel(const double* __restrict__ q, long long n_slots, long long cap, int my_rank, int D, int axis,
                     double lo_cov, double hi_cov, int k, const int64_t* __restrict__ idx_local,
-                    const double* __restrict__ dist, const int64_t* __restrict__ l2g, PeerPtrs rb) {
+                    const double* __restrict__ dist, const int64_t* __restrict__ l2g, PeerPtrs rb,
+                    unsigned long long* __restrict__ fails) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
   const long long src = i / cap, t = i - src * cap;
@@ -345,8 +346,35 @@ finalize_p2p_kernel(const double* __restrict__ q, long long n_slots, long long c
   const double margin = fmin(y - lo_cov, hi_cov - y);
   // no certificate (the k-th distance reaches beyond the region this rank covers, or fewer than k points): the index
   // word of entry 0 says so (-2; a missing neighbour is -1) -- two words per neighbour over NVLink instead of 2k + 1
+  const bool certified = full && kth < margin;
   row[0] = __double_as_longlong(d0);
-  row[ws] = (full && kth < margin) ? g0 : -2;
+  row[ws] = certified ? g0 : -2;
+  if (!certified && fails) atomicAdd(fails + src, 1ull);  // per asking rank (rare)
+}
+
+// counts -> the same place in EVERY peer's flag block (thread p stores to peer p)
+__global__ void share_counts_kernel(const unsigned long long* __restrict__ vals, int ncols, PeerPtrs fl, long long dst_off,
+                                    int n_ranks) {
+  const int p = threadIdx.x;
+  if (p >= n_ranks) return;
+  int64_t* dst = reinterpret_cast<int64_t*>(fl.p[p]) + dst_off;
+  for (int a = 0; a < ncols; a++) dst[a] = (int64_t)vals[a];
+}
+
+// flags[rows][cols]: column sums (per asking rank), their maximum -> *worst
+__global__ void worst_count_kernel(const int64_t* __restrict__ flags, int rows, int cols, int64_t* __restrict__ worst) {
+  long long best = 0;
+  for (int a = threadIdx.x; a < cols; a += 32) {
+    long long sum = 0;
+    for (int r = 0; r < rows; r++) sum += flags[(long long)r * cols + a];
+    best = sum > best ? sum : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+    best = ob > best ? ob : best;
+  }
+  if (threadIdx.x == 0) *worst = best;
 }
 
 // result block [2k][n_ranks][cap] (word-major; allocated with 2k+1 rows) -> the caller's arrays; slot (r, t) is valid for t < min(cursor[r], cap)
@@ -406,7 +434,7 @@ POMP_API int pomp_shard_route_p2p(const double* q, int64_t nq, int32_t dim, int3
 POMP_API int pomp_shard_finalize_p2p(const double* q, int64_t cap, int32_t n_ranks, int32_t my_rank, int32_t dim,
                                      int32_t axis, double lo_cov, double hi_cov, int32_t k, const int64_t* idx_local,
                                      const double* dist, const int64_t* local_to_global,
-                                     const uint64_t* peer_result_blocks_h, void* stream) {
+                                     const uint64_t* peer_result_blocks_h, uint64_t* fails_per_asker, void* stream) {
   POMP_REQUIRE(cap >= 0 && k >= 1 && dim >= 1 && axis >= 0 && axis < dim && n_ranks >= 1 && n_ranks <= SHARD_MAX_RANKS,
                "bad arguments to pomp_shard_finalize_p2p");
   if (cap == 0) return POMP_OK;
@@ -415,7 +443,28 @@ POMP_API int pomp_shard_finalize_p2p(const double* q, int64_t cap, int32_t n_ran
   for (int r = 0; r < SHARD_MAX_RANKS; r++) P.p[r] = r < n_ranks ? (void*)(uintptr_t)peer_result_blocks_h[r] : nullptr;
   const long long n = (long long)n_ranks * cap;
   LAUNCH(finalize_p2p_kernel, (int)((n + 255) / 256), 256, 0, (cudaStream_t)stream, q, n, (long long)cap, my_rank, dim,
-         axis, lo_cov, hi_cov, k, idx_local, dist, local_to_global, P);
+         axis, lo_cov, hi_cov, k, idx_local, dist, local_to_global, P, (unsigned long long*)fails_per_asker);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+// vals[ncols] (device) -> words [dst_offset, dst_offset + ncols) of every peer's flag block
+POMP_API int pomp_shard_share_counts_p2p(const uint64_t* vals, int32_t ncols, const uint64_t* peer_flag_blocks_h,
+                                         int64_t dst_offset, int32_t n_ranks, void* stream) {
+  POMP_REQUIRE(vals && peer_flag_blocks_h && ncols >= 1 && dst_offset >= 0 && n_ranks >= 1 && n_ranks <= SHARD_MAX_RANKS,
+               "bad arguments to pomp_shard_share_counts_p2p");
+  PeerPtrs P;
+  for (int r = 0; r < SHARD_MAX_RANKS; r++) P.p[r] = r < n_ranks ? (void*)(uintptr_t)peer_flag_blocks_h[r] : nullptr;
+  LAUNCH(share_counts_kernel, 1, SHARD_MAX_RANKS, 0, (cudaStream_t)stream, (const unsigned long long*)vals, ncols, P,
+         (long long)dst_offset, n_ranks);
+  CHECK_LAUNCH();
+  return POMP_OK;
+}
+
+// flags[rows][cols] (device): *worst = max over columns of the column sums
+POMP_API int pomp_shard_worst_count(const int64_t* flags, int32_t rows, int32_t cols, int64_t* worst, void* stream) {
+  POMP_REQUIRE(flags && worst && rows >= 1 && cols >= 1, "bad arguments to pomp_shard_worst_count");
+  LAUNCH(worst_count_kernel, 1, 32, 0, (cudaStream_t)stream, flags, rows, cols, worst);
   CHECK_LAUNCH();
   return POMP_OK;
 }

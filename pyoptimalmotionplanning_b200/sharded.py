@@ -463,6 +463,13 @@ class SpatialShardedNearestNeighbors(object):
         self._rb.zero_()
         self._rq_ptrs = (C.c_uint64 * G)(*[int(p) for p in self._rq_h.buffer_ptrs])
         self._rb_ptrs = (C.c_uint64 * G)(*[int(p) for p in self._rb_h.buffer_ptrs])
+        # deferred counts of a step, replicated on every rank by peer stores: [parity][G owners + 1 (route overflow)][G askers]
+        self._fl = symm.empty(2 * (G + 1) * G, dtype=torch.int64, device=dev)
+        self._fl_h = symm.rendezvous(self._fl, group)
+        self._fl.zero_()
+        self._fl_ptrs = (C.c_uint64 * G)(*[int(p) for p in self._fl_h.buffer_ptrs])
+        self._p2p_step = 0
+        self._bounds_c = (C.c_double * max(G - 1, 1))(*[float(x) for x in self.bounds])
         self._perm = torch.empty(G * cap, dtype=torch.int64, device=dev)
         torch.cuda.synchronize()
         self._rq_h.barrier(channel=0)
@@ -471,8 +478,8 @@ class SpatialShardedNearestNeighbors(object):
     def knearest_p2p(self, q, k, slack=1.04, fallback_slots=4096, _trace=None):
         """knearest_fast() with the two all-to-alls replaced by NVLink stores from the routing / finalize kernels into
         the peers' receive buffers (torch symmetric memory supplies the mapped peer pointers and the device barrier):
-        route+send is ONE kernel, finalize+return is ONE kernel, two barriers per step, no NCCL call on the data
-        path (one tiny all_reduce tells whether any query was deferred).  Same answers."""
+        route+send is ONE kernel, finalize+return is ONE kernel, two barriers per step, no NCCL call in the step (the
+        deferred counts travel as peer stores ahead of the second barrier).  Same answers."""
         return self.knearest_p2p_async(q, k, slack, fallback_slots, _trace).wait()
 
     def knearest_p2p_async(self, q, k, slack=1.04, fallback_slots=4096, _trace=None):
@@ -498,12 +505,17 @@ class SpatialShardedNearestNeighbors(object):
         cap = int(nq / G * slack) + 1024
         n_slots = G * cap
         self._p2p_setup(cap, k, dev)
-        ctr = torch.zeros(72, dtype=torch.int64, device=dev)
+        ctr = torch.zeros(72 + 64, dtype=torch.int64, device=dev)   # [0, G) cursors, [64] deferred, [72, 72 + G) fails
         dlist = torch.empty(max(nq, 1), dtype=torch.int64, device=dev)
-        b = (C.c_double * max(G - 1, 1))(*[float(x) for x in self.bounds])
+        b = self._bounds_c
+        par_off = (self._p2p_step & 1) * (G + 1) * G
+        self._p2p_step += 1
         check(lib, lib.pomp_shard_route_p2p(C.c_void_p(q.data_ptr()), nq, D, ax, b, G, self.rank, cap,
                                             C.c_void_p(ctr.data_ptr()), self._rq_ptrs, C.c_void_p(self._perm.data_ptr()),
                                             C.c_void_p(dlist.data_ptr()), nq, C.c_void_p(st)))
+        # my route overflow -> row G, column `rank` of every rank's flag block
+        check(lib, lib.pomp_shard_share_counts_p2p(C.c_void_p(ctr.data_ptr() + 64 * 8), 1, self._fl_ptrs,
+                                                   par_off + G * G + self.rank, G, C.c_void_p(st)))
         mark("route+send kernel")
         self._rq_h.barrier(channel=0)
         mark("barrier")
@@ -512,7 +524,11 @@ class SpatialShardedNearestNeighbors(object):
         mark("local_search")
         check(lib, lib.pomp_shard_finalize_p2p(C.c_void_p(recvq.data_ptr()), cap, G, self.rank, D, ax, float(self.lo_cov),
                                                float(self.hi_cov), k, C.c_void_p(il.data_ptr()), C.c_void_p(dl.data_ptr()),
-                                               C.c_void_p(self.l2g.data_ptr()), self._rb_ptrs, C.c_void_p(st)))
+                                               C.c_void_p(self.l2g.data_ptr()), self._rb_ptrs,
+                                               C.c_void_p(ctr.data_ptr() + 72 * 8), C.c_void_p(st)))
+        # the queries I could not certify, per asking rank -> row `rank` of every rank's flag block
+        check(lib, lib.pomp_shard_share_counts_p2p(C.c_void_p(ctr.data_ptr() + 72 * 8), G, self._fl_ptrs,
+                                                   par_off + self.rank * G, G, C.c_void_p(st)))
         mark("finalize+return kernel")
         self._rb_h.barrier(channel=1)
         mark("barrier")
@@ -523,10 +539,13 @@ class SpatialShardedNearestNeighbors(object):
                                              C.c_void_p(ctr.data_ptr()), C.c_void_p(idx.data_ptr()),
                                              C.c_void_p(dst.data_ptr()), C.c_void_p(dlist.data_ptr()), nq, C.c_void_p(st)))
         mark("unpack")
-        worst = dcount.clone()
-        if G > 1:
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
-        mark("deferred-count all_reduce")
+        # the largest deferred count of any rank, from the flag block every rank now holds: no collective.  (An upper
+        # bound: an owner also counts stale padding slots it could not certify; that can only trigger a fallback that
+        # finds nothing to do.)
+        worst = torch.empty(1, dtype=torch.int64, device=dev)
+        check(lib, lib.pomp_shard_worst_count(C.c_void_p(self._fl.data_ptr() + par_off * 8), G + 1, G,
+                                              C.c_void_p(worst.data_ptr()), C.c_void_p(st)))
+        mark("deferred-count reduce")
         # (own, worst rank's) deferred counts into one of a few rotating pinned buffers, an event behind the copies
         pool = getattr(self, "_pin_pool", None)
         if pool is None:
