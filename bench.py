@@ -258,8 +258,8 @@ def workload_config(gpus):
                            "node set (2^%d points) sharded spatially over %d GPUs (slabs + halo); every query routed to "
                            "the owning GPU and its packed (distance, index) record returned, both by NVLink stores from "
                            "the routing / finalize kernels into peer memory (node_sharded.exchange = p2p; NCCL all_to_all "
-                           "when symmetric memory is unavailable), two device barriers and one all_reduce (deferred "
-                           "count) per batch, uncertified remainder through an all_gather fallback; batches streamed "
+                           "when symmetric memory is unavailable), two device barriers per batch and no NCCL call (the "
+                           "deferred counts are peer stores too), uncertified remainder through an all_gather fallback; batches streamed "
                            "(batch i is validated on the host after batch i+1 was issued); replicated-index number "
                            "under replicated_index" % (LOG2_N, gpus)}
 
