@@ -1842,8 +1842,11 @@ POMP_API int pomp_nn_knearest_h(pomp_nn* h, const double* q_h, int64_t nq, int32
       CUDA_TRY(cudaEventRecord(h->pipe_ev[2 * c], h->copy_in));
       if (trace) CUDA_TRY(cudaEventRecord(tev[1 + 3 * c], h->copy_in));
       CUDA_TRY(cudaStreamWaitEvent(st, h->pipe_ev[2 * c], 0));
-      POMP_TRY(knn_chunk(h, c, h->q_dev.p + b * h->D, m, k, h->out_idx.p + b * k, h->out_dist.p + b * k,
-                         count_h ? h->out_cnt.p + b : nullptr, st));
+      h->pipe_chunks_active = nchunk;  // strip_eligible: a chunk is a fraction of the batch (gather kernels below 64 / tile)
+      const int chunk_status = knn_chunk(h, c, h->q_dev.p + b * h->D, m, k, h->out_idx.p + b * k, h->out_dist.p + b * k,
+                                         count_h ? h->out_cnt.p + b : nullptr, st);
+      h->pipe_chunks_active = 0;
+      POMP_TRY(chunk_status);
       CUDA_TRY(cudaEventRecord(h->pipe_ev[2 * c + 1], st));
       if (trace) CUDA_TRY(cudaEventRecord(tev[2 + 3 * c], st));
       CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->pipe_ev[2 * c + 1], 0));

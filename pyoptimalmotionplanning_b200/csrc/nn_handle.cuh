@@ -103,6 +103,7 @@ struct pomp_nn {
   cudaStream_t stream = nullptr;  // used by the *_h variants
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined *_h path
   std::vector<cudaEvent_t> pipe_ev;
+  int pipe_chunks_active = 0;   // > 1 while a chunk of the pipelined *_h path is being searched
   double pipeline_chunks = 6;   // measured on B200 (2^20 2-D queries): 4: 0.575, 6: 0.552, 8: 0.567 ms end to end
   double pipeline_shape = 1;    // chunk sizes: 0 = shrinking (C+1, C, ..., 2), 1 = triangle
   // CUDA graphs of the per-chunk searches of the pipelined *_h path: with both copy engines busy every
