@@ -104,22 +104,49 @@ POMP_API int pomp_select_control(const pomp_dyn_desc* dyn, const pomp_metric_des
   return POMP_OK;
 }
 
-// ---- host-buffer variants (one-shot staging; planners call these once per iteration) --------
+// ---- host-buffer variants (planners call these once per iteration) ---------------------------------------------------
+// One call = pack the inputs into a pinned buffer, ONE async copy in, the kernel, ONE async copy of the packed outputs,
+// one stream synchronisation.  The staging (device + pinned, grow-only) and the stream persist per host thread and
+// device.  (First version: cudaMalloc + four blocking pageable copies in + three out + cudaFree per call, ~0.1 ms.)
 namespace {
-struct Staging {
-  void* p = nullptr;
-  ~Staging() {
-    if (p) cudaFree(p);
+struct HostStage {
+  int device = -1;
+  unsigned char* dev = nullptr;
+  unsigned char* pin = nullptr;
+  size_t cap = 0;
+  cudaStream_t st = nullptr;
+  ~HostStage() {  // process exit: the context may already be gone, errors are ignored
+    if (dev) cudaFree(dev);
+    if (pin) cudaFreeHost(pin);
+    if (st) cudaStreamDestroy(st);
   }
-  int alloc(size_t bytes) {
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-    if (e != cudaSuccess) {
-      set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-      return e == cudaErrorMemoryAllocation ? POMP_ERR_NOMEM : POMP_ERR_CUDA;
+  int reserve(int device_now, size_t bytes) {
+    if (device_now != device) {
+      if (dev) cudaFree(dev);
+      if (pin) cudaFreeHost(pin);
+      if (st) cudaStreamDestroy(st);
+      dev = pin = nullptr;
+      st = nullptr;
+      cap = 0;
+      device = device_now;
     }
+    if (!st) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (bytes <= cap) return POMP_OK;
+    if (dev) cudaFree(dev);
+    if (pin) cudaFreeHost(pin);
+    dev = pin = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 2 + 4096;
+    if (cudaMalloc((void**)&dev, want) != cudaSuccess || cudaMallocHost((void**)&pin, want) != cudaSuccess) {
+      set_error("staging allocation of %zu bytes failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+      return POMP_ERR_NOMEM;
+    }
+    cap = want;
     return POMP_OK;
   }
 };
+thread_local HostStage g_stage;
+inline size_t up8(size_t n) { return (n + 7) / 8 * 8; }
 }  // namespace
 
 POMP_API int pomp_next_state_h(const pomp_dyn_desc* dyn, const double* x_h, const double* u_h, int64_t n,
@@ -131,16 +158,17 @@ POMP_API int pomp_next_state_h(const pomp_dyn_desc* dyn, const double* x_h, cons
   if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   POMP_TRY(ensure_device(dev));
   const int XF = dyn->x_dim + (dyn->cost_kind != POMP_COST_NONE);
-  size_t bx = sizeof(double) * (size_t)n * XF, bu = sizeof(double) * (size_t)n * dyn->u_dim;
-  Staging s;
-  POMP_TRY(s.alloc(2 * bx + bu));
-  double* dx = (double*)s.p;
-  double* dout = dx + (size_t)n * XF;
-  double* du = dout + (size_t)n * XF;
-  CUDA_TRY(cudaMemcpy(dx, x_h, bx, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(du, u_h, bu, cudaMemcpyHostToDevice));
-  POMP_TRY(pomp_next_state(dyn, dx, du, n, dout, nullptr));
-  CUDA_TRY(cudaMemcpy(xnext_h, dout, bx, cudaMemcpyDeviceToHost));
+  const size_t bx = sizeof(double) * (size_t)n * XF, bu = sizeof(double) * (size_t)n * dyn->u_dim;
+  HostStage& S = g_stage;
+  POMP_TRY(S.reserve(dev, 2 * bx + bu));
+  // layout (device and pinned alike): x | u | xnext
+  memcpy(S.pin, x_h, bx);
+  memcpy(S.pin + bx, u_h, bu);
+  CUDA_TRY(cudaMemcpyAsync(S.dev, S.pin, bx + bu, cudaMemcpyHostToDevice, S.st));
+  POMP_TRY(pomp_next_state(dyn, (const double*)S.dev, (const double*)(S.dev + bx), n, (double*)(S.dev + bx + bu), S.st));
+  CUDA_TRY(cudaMemcpyAsync(S.pin + bx + bu, S.dev + bx + bu, bx, cudaMemcpyDeviceToHost, S.st));
+  CUDA_TRY(cudaStreamSynchronize(S.st));
+  memcpy(xnext_h, S.pin + bx + bu, bx);
   return POMP_OK;
 }
 
@@ -155,24 +183,25 @@ POMP_API int pomp_select_control_h(const pomp_dyn_desc* dyn, const pomp_metric_d
   if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   POMP_TRY(ensure_device(dev));
   const int XF = dyn->x_dim + (dyn->cost_kind != POMP_COST_NONE);
-  size_t bx = sizeof(double) * (size_t)B * XF, bu = sizeof(double) * (size_t)B * S * dyn->u_dim;
-  size_t bv = (size_t)B * S, bb = sizeof(int32_t) * (size_t)B, bd = sizeof(double) * (size_t)B;
-  Staging s;
-  POMP_TRY(s.alloc(3 * bx + bu + bd + bb + bv + 64));
-  double* dx = (double*)s.p;
-  double* dxd = dx + (size_t)B * XF;
-  double* dxb = dxd + (size_t)B * XF;
-  double* du = dxb + (size_t)B * XF;
-  double* ddist = du + (size_t)B * S * dyn->u_dim;
-  int32_t* dbest = (int32_t*)(ddist + B);
-  uint8_t* dvalid = (uint8_t*)(dbest + B);
-  CUDA_TRY(cudaMemcpy(dx, x_h, bx, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(dxd, xdes_h, bx, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(du, u_h, bu, cudaMemcpyHostToDevice));
-  if (valid_h) CUDA_TRY(cudaMemcpy(dvalid, valid_h, bv, cudaMemcpyHostToDevice));
-  POMP_TRY(pomp_select_control(dyn, metric, dx, dxd, du, valid_h ? dvalid : nullptr, B, S, dbest, dxb, ddist, nullptr));
-  CUDA_TRY(cudaMemcpy(best_h, dbest, bb, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(xnext_best_h, dxb, bx, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(dist_best_h, ddist, bd, cudaMemcpyDeviceToHost));
+  const size_t bx = sizeof(double) * (size_t)B * XF, bu = sizeof(double) * (size_t)B * S * dyn->u_dim;
+  const size_t bv = up8((size_t)B * S), bb = up8(sizeof(int32_t) * (size_t)B), bd = sizeof(double) * (size_t)B;
+  // layout (device and pinned alike): inputs x | xdes | u | valid, outputs xbest | dist | best
+  const size_t o_x = 0, o_xd = bx, o_u = 2 * bx, o_v = 2 * bx + bu, in_bytes = o_v + bv;
+  const size_t o_xb = in_bytes, o_d = o_xb + bx, o_b = o_d + bd, out_bytes = bx + bd + bb;
+  HostStage& G = g_stage;
+  POMP_TRY(G.reserve(dev, in_bytes + out_bytes));
+  memcpy(G.pin + o_x, x_h, bx);
+  memcpy(G.pin + o_xd, xdes_h, bx);
+  memcpy(G.pin + o_u, u_h, bu);
+  if (valid_h) memcpy(G.pin + o_v, valid_h, (size_t)B * S);
+  CUDA_TRY(cudaMemcpyAsync(G.dev, G.pin, valid_h ? in_bytes : o_v, cudaMemcpyHostToDevice, G.st));
+  POMP_TRY(pomp_select_control(dyn, metric, (const double*)(G.dev + o_x), (const double*)(G.dev + o_xd),
+                               (const double*)(G.dev + o_u), valid_h ? (const uint8_t*)(G.dev + o_v) : nullptr, B, S,
+                               (int32_t*)(G.dev + o_b), (double*)(G.dev + o_xb), (double*)(G.dev + o_d), G.st));
+  CUDA_TRY(cudaMemcpyAsync(G.pin + o_xb, G.dev + o_xb, out_bytes, cudaMemcpyDeviceToHost, G.st));
+  CUDA_TRY(cudaStreamSynchronize(G.st));
+  memcpy(xnext_best_h, G.pin + o_xb, bx);
+  memcpy(dist_best_h, G.pin + o_d, bd);
+  memcpy(best_h, G.pin + o_b, sizeof(int32_t) * (size_t)B);
   return POMP_OK;
 }
