@@ -126,7 +126,8 @@ int64_t pomp_nn_size(const pomp_nn* h);
                    2-D nearest() batches; "block_search" (1; 2 = also in 3-D), "block_need": fixed block of cells +
                    certificate in 2-D; "warp_search" (1 = where it wins, 2 = always, 0 = never), "warp_lanes" (32; 8,
                    16), "warp_need": the warp-per-query shell kernel; "se2_fast" (1): compile-time SE(2) kernel;
-                   "bf_tiled" (1): shared-memory tiled brute force for Euclidean k = 1 batches
+                   "bf_tiled" (1): shared-memory tiled brute force for Euclidean k = 1 batches; "single_radius" (1):
+                   one-launch path of a single neighbors() query in the brute-force regime
      host pipeline "pipeline_chunks" (6), "pipeline_shape" (1 = triangle), "use_graphs" (1): the *_h entry points
      measurement   "profile" (0): CUDA events around the dominant search kernel, read back with
                    pomp_nn_get_stat("search_kernel_ms" / "search_kernel_launches") */

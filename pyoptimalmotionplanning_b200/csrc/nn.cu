@@ -427,6 +427,54 @@ __global__ void bf_radius_kernel(const double* __restrict__ pts, long long n, po
   if (!FILL && lane == 0) counts[warp] = (int)cnt;
 }
 
+// Single radius query of the planner loops (SST's pickNode / nodeLocallyBest, EST): the query travels in the kernel
+// arguments, every block scans its share of the nodes, hits are appended (warp-aggregated) to a list in MAPPED HOST
+// memory and the last block publishes the count: one launch + one stream synchronisation per neighbors() call, the
+// host sorts the handful of hits into insertion order.  (The general path: count kernel, 3-kernel scan, two copies, a
+// synchronisation for the total, fill kernel, two more copies.)
+constexpr int RADBOX_CAP = 8192;
+struct RadBox {
+  unsigned int count;
+  int hits[RADBOX_CAP];
+};
+__global__ void bf_single_radius_kernel(const double* __restrict__ pts, long long n, pomp_metric_desc m,
+                                        const uint8_t* __restrict__ skip, QueryArg qa, double radius, int inclusive,
+                                        unsigned int* counters /* [0] hits, [1] ticket */, RadBox* out) {
+  const int D = m.dim;
+  const int lane = threadIdx.x & 31;
+  double p[POMP_MAX_DIM];
+  // whole warps stay in the loop together (ballot): the bound is rounded up to a multiple of 32 per warp
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+    const long long i = i0 + lane;
+    bool hit = false;
+    if (i < n && !(skip && skip[i])) {
+      for (int j = 0; j < D; j++) p[j] = __ldg(pts + i * D + j);
+      const double d = metric_eval(m, p, qa.v);
+      hit = inclusive ? (d <= radius) : (d < radius);
+    }
+    const unsigned mask = __ballot_sync(FULL_MASK, hit);
+    if (mask) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(counters, (unsigned)__popc(mask));
+      base = __shfl_sync(FULL_MASK, base, 0);
+      const unsigned int at = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+      if (hit && at < (unsigned)RADBOX_CAP) out->hits[at] = (int)i;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(counters + 1, 1u);
+    if (t == gridDim.x - 1) {
+      out->count = *(volatile unsigned int*)counters;
+      counters[0] = 0;  // re-arm for the next call
+      counters[1] = 0;
+      __threadfence_system();
+    }
+  }
+}
+
 // ============================================================================ grid build kernels
 // DC > 0: compile-time dimension (bounds in registers, compare + select: sm_100 has no FP64 min / max instruction and
 // fmin / fmax expand to a NaN-aware sequence; `v < mn ? v : mn` ignores NaN coordinates the same way); DC = 0: any D
@@ -1457,6 +1505,10 @@ POMP_API int pomp_nn_create(const pomp_metric_desc* metric, int64_t capacity_hin
   if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->mailbox_d, h->mailbox_h, 0);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaHostAlloc(&h->radbox_h, sizeof(RadBox), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->radbox_d, h->radbox_h, 0);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->rad_counters, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->rad_counters, 0, 2 * sizeof(unsigned int));
   if (e != cudaSuccess) {
     set_error("pomp_nn_create: %s", cudaGetErrorString(e));
     delete h;
@@ -1479,6 +1531,8 @@ POMP_API int pomp_nn_destroy(pomp_nn* h) {
   if (h->d_skip) cudaFree(h->d_skip);
   if (h->mailbox_h) cudaFreeHost(h->mailbox_h);
   if (h->ticket) cudaFree(h->ticket);
+  if (h->radbox_h) cudaFreeHost(h->radbox_h);
+  if (h->rad_counters) cudaFree(h->rad_counters);
   if (h->stream) cudaStreamDestroy(h->stream);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->rw_pin) cudaFreeHost(h->rw_pin);
@@ -1631,6 +1685,7 @@ POMP_API int pomp_nn_set_param(pomp_nn* h, const char* name, double value) {
   else if (s == "max_tail") h->max_tail = value;
   else if (s == "block_search") h->block_search = value;
   else if (s == "block_need") h->block_need = value;
+  else if (s == "single_radius") h->single_radius = value;
   else if (s == "warp_search") h->warp_search = value;
   else if (s == "warp_need") h->warp_need = value;
   else if (s == "warp_lanes") h->warp_lanes = value;
@@ -1966,6 +2021,44 @@ POMP_API int pomp_nn_neighbors_h(pomp_nn* h, const double* q_h, int64_t nq, doub
     offsets_h[0] = 0;
     if (needed_h) *needed_h = 0;
     return POMP_OK;
+  }
+  if (nq == 1 && h->single_radius != 0) {
+    // planner fast path (node sets of the brute-force regime): see bf_single_radius_kernel
+    POMP_TRY(nn_flush(h, st));
+    const int64_t n = h->n_dev;
+    bool use_grid = false;
+    POMP_TRY(want_grid(h, nq, &use_grid, st));
+    if (!use_grid) {
+      if (n == 0) {
+        offsets_h[0] = offsets_h[1] = 0;
+        if (needed_h) *needed_h = 0;
+        return POMP_OK;
+      }
+      QueryArg qa;
+      for (int j = 0; j < POMP_MAX_DIM; j++) qa.v[j] = j < h->D ? q_h[j] : 0.0;
+      int blocks = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)sm_count(h->device) * 2);
+      blocks = std::max(blocks, 1);
+      const int threads = n <= 256 ? 64 : 256;
+      LAUNCH(bf_single_radius_kernel, blocks, threads, 0, st, h->d_pts, (long long)n, h->metric, h->skip_ptr(), qa,
+             radius, inclusive, h->rad_counters, (RadBox*)h->radbox_d);
+      CHECK_LAUNCH();
+      CUDA_TRY(cudaStreamSynchronize(st));
+      RadBox* rb = (RadBox*)h->radbox_h;
+      const int64_t cnt = rb->count;
+      if (cnt <= RADBOX_CAP) {
+        if (needed_h) *needed_h = cnt;
+        offsets_h[0] = 0;
+        offsets_h[1] = cnt;
+        if (cnt > idx_capacity) {
+          set_error("radius query produced %lld hits, capacity %lld", (long long)cnt, (long long)idx_capacity);
+          return POMP_ERR_CAPACITY;
+        }
+        std::sort(rb->hits, rb->hits + cnt);   // neighbors() reports hits in insertion order
+        for (int64_t j = 0; j < cnt; j++) idx_h[j] = rb->hits[j];
+        return POMP_OK;
+      }
+      // more hits than the box holds: the general path answers
+    }
   }
   POMP_TRY(h->q_dev.reserve((size_t)nq * h->D));
   POMP_TRY(h->out_idx.reserve((size_t)std::max<int64_t>(idx_capacity, 1)));

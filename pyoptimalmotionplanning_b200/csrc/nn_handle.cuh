@@ -100,6 +100,11 @@ struct pomp_nn {
   void* mailbox_h = nullptr;
   void* mailbox_d = nullptr;
   unsigned int* ticket = nullptr;
+  // single radius query fast path: hit list in mapped pinned memory, device counters {hits, ticket}
+  void* radbox_h = nullptr;
+  void* radbox_d = nullptr;
+  unsigned int* rad_counters = nullptr;
+  double single_radius = 1;   // 0: every neighbors() call takes the general (count / scan / fill) path
   cudaStream_t stream = nullptr;  // used by the *_h variants
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined *_h path
   std::vector<cudaEvent_t> pipe_ev;

@@ -932,3 +932,32 @@ def test_warp_shell_kernel_masks_tail_ties_and_clusters(D, lanes):
     oi, od, oc = oracle.nn_knearest(m, few, qf, 32)
     assert (idx == oi).all() and (cnt == oc).all()
     assert cnt[3] == 0 and cnt[5] == 0 and (cnt[[0, 1, 2]] == 20).all()
+
+
+def test_single_radius_query_fast_path_matches_oracle():
+    """One neighbors() query in the brute-force regime: the one-launch path (hits appended in mapped host memory,
+    sorted on the host) against the oracle and against the general count / scan / fill path -- inclusive and
+    exclusive radius, generic metric, masks, and a query with more hits than the box holds (falls back)."""
+    rng = np.random.default_rng(31)
+    for m, D in ((MetricSpec.euclidean(2), 2), (_metrics()["se2"], 3), (MetricSpec.l1(3), 3)):
+        pts = rng.random((20000, D))
+        nn = _nn(m, pts)
+        ref = _nn(m, pts)
+        ref.set_param("single_radius", 0)
+        mask = (rng.random(20000) < 0.3).astype(np.uint8)
+        for masked in (False, True):
+            nn.set_mask(mask if masked else None)
+            ref.set_mask(mask if masked else None)
+            for r in (0.0, 0.02, 0.3, 5.0):                  # 5.0: every unmasked point (> 8192 hits)
+                for incl in (True, False):
+                    q = rng.random((1, D))
+                    off, hits = nn.neighbors(q, r, incl)
+                    roff, rhits = ref.neighbors(q, r, incl)
+                    assert (off == roff).all() and (hits == rhits).all(), (D, masked, r, incl)
+                    if m.kind != _abi.METRIC_GEODESIC_PRODUCT:     # product metrics: 2-ulp boundary, see above
+                        ooff, ohits = oracle.nn_neighbors(m, pts, q, r, incl, mask if masked else None)
+                        assert (off == ooff).all() and (hits == ohits).all(), (D, masked, r, incl)
+    # a point exactly at the radius: kd-tree semantics (d <= r) vs brute-force semantics (d < r)
+    nn = _nn(MetricSpec.euclidean(2), np.array([[0.0, 0.0], [3.0, 4.0], [6.0, 8.0]]))
+    assert nn.neighbors(np.array([[0.0, 0.0]]), 5.0, True)[1].tolist() == [0, 1]
+    assert nn.neighbors(np.array([[0.0, 0.0]]), 5.0, False)[1].tolist() == [0]
