@@ -474,6 +474,53 @@ __global__ void edge_check_control_kernel(SpaceDev s, pomp_dyn_desc dy, pomp_met
   ok[ei] = 1;
 }
 
+// ONE straight edge of a planner loop (EpsilonEdgeChecker.feasible(LinearInterpolator), edgechecker.py:20-30): the
+// endpoints travel in the kernel arguments, one block evaluates the reference's samples in parallel (a conjunction:
+// order is free), the answer lands in mapped host memory -- one launch + one synchronisation per call.  (The batch
+// path for n = 1: two pageable copies in, the kernel, one copy out.)
+struct EdgeArg {
+  double a[POMP_MAX_DIM], b[POMP_MAX_DIM];
+};
+__global__ void __launch_bounds__(128)
+edge_one_kernel(SpaceDev s, EdgeArg e, double res, int* __restrict__ out) {
+  __shared__ int fail;
+  const int dim = s.dim;
+  if (threadIdx.x == 0) fail = 0;
+  __syncthreads();
+  double l = 0.0;
+  for (int j = 0; j < dim; j++) {
+    const double t = e.a[j] - e.b[j];
+    l = l + t * t;
+  }
+  l = sqrt(l);
+  const long long k = edge_samples(s, l, res);
+  if (k < 0) {
+    if (threadIdx.x == 0) {
+      *out = 0;
+      __threadfence_system();
+    }
+    return;
+  }
+  if (threadIdx.x == 0 && !feasible_pt(s, e.a)) fail = 1;
+  if (threadIdx.x == 32 && !feasible_pt(s, e.b)) fail = 1;
+  __syncthreads();
+  if (!fail) {
+    const double kk2 = (double)(k + 2);
+    for (long long i = threadIdx.x; i < k; i += blockDim.x) {
+      if (*(volatile int*)&fail) break;
+      const double u = (double)(i + 1) / kk2;
+      double x[POMP_MAX_DIM];
+      for (int j = 0; j < dim; j++) x[j] = e.a[j] + u * (e.b[j] - e.a[j]);
+      if (!feasible_pt(s, x)) fail = 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *out = fail ? 0 : 1;
+    __threadfence_system();
+  }
+}
+
 // ============================================================================ host: space handle
 static int build_obstacle_grid(pomp_space* sp, const pomp_space_desc* d, cudaStream_t st) {
   SpaceDev& s = sp->dev;
@@ -675,12 +722,13 @@ POMP_API int pomp_space_create(const pomp_space_desc* d, int device, pomp_space*
   }
   s.boxes = sp->d_boxes;
   s.circles = sp->d_circles;
-  if (cudaHostAlloc((void**)&sp->overflow_h, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+  // mapped pinned words: [0] the overflow flag, [4] the answer of the single-edge fast path
+  if (cudaHostAlloc((void**)&sp->overflow_h, 16 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer((void**)&s.overflow, sp->overflow_h, 0) != cudaSuccess) {
     set_error("mapped flag allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(POMP_ERR_CUDA);
   }
-  *sp->overflow_h = 0;
+  for (int j = 0; j < 16; j++) sp->overflow_h[j] = 0;
   int rc = build_obstacle_grid(sp, d, sp->stream);
   if (rc != POMP_OK) return fail(rc);
   // obstacle tables were copied on the default stream; queries run on non-blocking streams
@@ -897,6 +945,19 @@ POMP_API int pomp_edge_check_h(pomp_space* sp, const double* a_h, const double* 
   if (!g.ok) return POMP_ERR_CUDA;
   if (n == 0) return POMP_OK;
   cudaStream_t st = sp->stream;
+  if (n == 1) {
+    POMP_REQUIRE(resolution > 0.0, "resolution must be positive");
+    EdgeArg e;
+    for (int j = 0; j < POMP_MAX_DIM; j++) {
+      e.a[j] = j < sp->dev.dim ? a_h[j] : 0.0;
+      e.b[j] = j < sp->dev.dim ? b_h[j] : 0.0;
+    }
+    LAUNCH(edge_one_kernel, 1, 128, 0, st, sp->dev, e, resolution, sp->dev.overflow + 4);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ok_h[0] = sp->overflow_h[4] ? 1 : 0;
+    return space_overflow_check(sp);
+  }
   H2D(sp->in_a, a_h, n * sp->dev.dim, double);
   H2D(sp->in_b, b_h, n * sp->dev.dim, double);
   POMP_TRY(sp->out_ok.reserve((size_t)n));
