@@ -729,6 +729,13 @@ POMP_API int pomp_space_create(const pomp_space_desc* d, int device, pomp_space*
     return fail(POMP_ERR_CUDA);
   }
   for (int j = 0; j < 16; j++) sp->overflow_h[j] = 0;
+  // mapped scratch of the single-path / single-control-edge calls of planner loops (inputs read and the answer
+  // written by the kernel over PCIe: no copies around a 1-thread kernel)
+  if (cudaHostAlloc((void**)&sp->map_h, POMP_MAP_BYTES, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&sp->map_d, sp->map_h, 0) != cudaSuccess) {
+    set_error("mapped scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(POMP_ERR_CUDA);
+  }
   int rc = build_obstacle_grid(sp, d, sp->stream);
   if (rc != POMP_OK) return fail(rc);
   // obstacle tables were copied on the default stream; queries run on non-blocking streams
@@ -752,6 +759,7 @@ POMP_API int pomp_space_destroy(pomp_space* sp) {
   if (sp->d_fine) cudaFree(sp->d_fine);
   if (sp->stream) cudaStreamDestroy(sp->stream);
   if (sp->overflow_h) cudaFreeHost(sp->overflow_h);
+  if (sp->map_h) cudaFreeHost(sp->map_h);
   delete sp;
   return POMP_OK;
 }
@@ -992,6 +1000,18 @@ POMP_API int pomp_edge_check_control_h(pomp_space* sp, const pomp_dyn_desc* dyn,
   if (!g.ok) return POMP_ERR_CUDA;
   if (n == 0) return POMP_OK;
   cudaStream_t st = sp->stream;
+  if (n == 1 && sp->map_h) {
+    // one control edge of a planner loop: state, control and the answer in mapped host memory
+    unsigned char* mh = sp->map_h;
+    unsigned char* md = sp->map_d;
+    memcpy(mh + 256, x_h, sizeof(double) * dyn->x_dim);
+    memcpy(mh + 512, u_h, sizeof(double) * dyn->u_dim);
+    POMP_TRY(pomp_edge_check_control(sp, dyn, geodesic, (const double*)(md + 256), (const double*)(md + 512), 1,
+                                     resolution, (uint8_t*)md, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ok_h[0] = mh[0];
+    return space_overflow_check(sp);
+  }
   H2D(sp->in_a, x_h, n * dyn->x_dim, double);
   H2D(sp->in_b, u_h, n * dyn->u_dim, double);
   POMP_TRY(sp->out_ok.reserve((size_t)n));

@@ -141,6 +141,8 @@ __device__ __forceinline__ long long edge_samples(const SpaceDev& s, double l, d
 
 }  // namespace pomp
 
+constexpr size_t POMP_MAP_BYTES = 16384;
+
 struct pomp_space {
   int device = 0;
   pomp::SpaceDev dev;
@@ -162,6 +164,8 @@ struct pomp_space {
   pomp::DevBuf<int> rm_flag, rm_pos;
   pomp::DevBuf<long long> rm_scan;
   int* overflow_h = nullptr;  // host alias of dev.overflow
+  unsigned char* map_h = nullptr;  // mapped pinned scratch (POMP_MAP_BYTES) of the single-edge host calls, host / device alias
+  unsigned char* map_d = nullptr;
 };
 
 // after a stream synchronisation: turns a raised overflow flag into POMP_ERR_INVALID (and clears it)
