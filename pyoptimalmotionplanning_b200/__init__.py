@@ -16,8 +16,9 @@ from .structures import NearestNeighbors, ProjectionHashDensity
 from .spaces import DeviceSpace, EpsilonEdgeChecker, DeviceControlSpace, BatchedRandomControlSelector
 from .install import install, uninstall, make_checker
 from .sst import SSTStarForest
+from .roadmap import DeviceRoadmap
 from ._abi import PompError, load_library
 
 __all__ = ["MetricSpec", "SpaceSpec", "DynamicsSpec", "metric_from_pomp", "space_from_pomp", "dynamics_from_pomp",
            "NearestNeighbors", "ProjectionHashDensity", "DeviceSpace", "EpsilonEdgeChecker", "DeviceControlSpace",
-           "BatchedRandomControlSelector", "SSTStarForest", "install", "uninstall", "make_checker", "PompError", "load_library"]
+           "BatchedRandomControlSelector", "SSTStarForest", "DeviceRoadmap", "install", "uninstall", "make_checker", "PompError", "load_library"]
