@@ -1060,7 +1060,10 @@ def run_gpu(args):
         if world == 1:
             if not args.no_extras:
                 line["extras"] = run_extras(peak)
-                line["extras"].update(run_planner_extras())
+                try:
+                    line["extras"].update(run_planner_extras())
+                except Exception as e:   # planner-level extras need the staged reference copy; never fatal
+                    line["extras"]["planners"] = {"error": repr(e)[:200]}
             if not args.no_cpu:
                 cb = cpu_kdtree_run(2, 1, False)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "value_1core")}
