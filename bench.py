@@ -1059,7 +1059,10 @@ def run_gpu(args):
             line["striped_units"] = striped
         if world == 1:
             if not args.no_extras:
-                line["extras"] = run_extras(peak)
+                try:
+                    line["extras"] = run_extras(peak)
+                except Exception as e:   # the headline line must survive a failing extra
+                    line["extras"] = {"error": repr(e)[:300]}
                 try:
                     line["extras"].update(run_planner_extras())
                 except Exception as e:   # planner-level extras need the staged reference copy; never fatal
